@@ -1,0 +1,1117 @@
+// hevce_core.h -- the HEVC intra still-image encoder of this repository: every stage of the hot path
+// (reference samples, 35 predictors, integer transforms, simplified RDOQ, reconstruction, CABAC trial coding,
+// CU quadtree decision, bitstream commit) as code for ONE CTA that encodes ONE picture.
+//
+// The file is compiled by nvcc into the sm_100a kernel (hevce_kernel.cu).  It contains no CPU fallback: the
+// product library only ever runs it on the GPU.  For development the same source is also compiled by g++ into a
+// single-threaded *simulator* of the CTA (tests/sim/, test infrastructure only), where every PAR_FOR phase runs
+// its work items in a permuted order; bit-exactness under permutation shows the phases are race-free.
+//
+// Execution model ("bulk-synchronous lanes"):
+//   * one CTA per picture, CTUs in raster order, CUs in z-order (the CABAC state threads through the whole
+//     picture, so this order is forced -- SURVEY.md section 7.3-1);
+//   * inside a CU node every rate-distortion candidate (35 modes x {one TU, four TUs, NxN PU round}) is one
+//     *lane* (= one thread): it runs the whole pixel pipeline and a private trial arithmetic coder started from
+//     the node's snapshot, and publishes (cost, coder state, contexts);
+//   * thread 0 takes the arg-min with the reference's "last minimum wins" order, the CTA copies the winner's
+//     reconstruction / levels / coder state into the live state;
+//   * after each CTU the final decision tree is re-encoded once by a byte-writing coder (commit pass).
+//
+// Behavioural parity target: /root/reference/src/HEVCe.c (cited as HEVCe.c:NNN).  Written from scratch.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HEVCE_HD __host__ __device__
+#else
+#define HEVCE_HD
+#endif
+
+namespace hevce {
+
+typedef uint8_t u8;
+typedef int16_t s16;
+typedef uint32_t u32;
+
+// ------------------------------------------------------------------------------------------------------------
+// sizes
+// ------------------------------------------------------------------------------------------------------------
+constexpr int CTU = 32;
+constexpr int NL = 128;            // candidate lanes per picture slot (= threads per CTA)
+constexpr int NMODE = 35;
+constexpr int NCTX = 142;          // context bytes, same offsets as the reference struct (HEVCe.c:745-759)
+constexpr int CTXW = 36;           // context words per lane (144 bytes)
+constexpr int WP = 65;             // pitch of the CTU reconstruction window (row 0 / col 0 = neighbours)
+constexpr int IMAX = 0x7fffffff;
+constexpr int LANE_ELEMS = CTU * CTU;
+
+enum { CX_SPLIT_CU = 0, CX_PART = 3, CX_YPM = 4, CX_UVPM = 5, CX_SPLIT_TU = 6, CX_YCBF = 9, CX_UVCBF = 11,
+       CX_LASTX = 16, CX_LASTY = 41, CX_SIGCG = 66, CX_SIG = 68, CX_ONE = 112, CX_ABS = 136 };
+
+HEVCE_HD inline int imin(int a, int b) { return a < b ? a : b; }
+HEVCE_HD inline int imax(int a, int b) { return a > b ? a : b; }
+HEVCE_HD inline int iclip(int v, int lo, int hi) { return imin(imax(v, lo), hi); }
+HEVCE_HD inline int iabs(int v) { return v < 0 ? -v : v; }
+HEVCE_HD inline int ilog2(int v) {   // v = 4, 8, 16, 32 -> 2..5
+    return v == 4 ? 2 : v == 8 ? 3 : v == 16 ? 4 : 5;
+}
+HEVCE_HD inline int bitlen(unsigned v) {
+#if defined(__CUDA_ARCH__)
+    return 32 - __clz((int)v);
+#else
+    return v ? 32 - __builtin_clz(v) : 0;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// constant tables (filled on the host by fill_tables(), copied to __constant__ and from there to shared memory)
+// ------------------------------------------------------------------------------------------------------------
+struct Tables {
+    u8 lps[64 * 4];        // rangeTabLps                                   (HEVCe.c:704-713)
+    u8 next_lps[128];      // (state<<1|mps) after an LPS                   (HEVCe.c:702)
+    u8 ctx_iv[144];        // context init values by byte offset            (HEVCe.c:763-777)
+    u8 scan4[3][16];       // in-CG scan, (y<<2)|x : diag / horizontal / vertical
+    u8 cgdiag[3][64];      // diagonal CG order for 2x2 / 4x4 / 8x8 CG grids, (cy<<3)|cx
+    u8 sigp4[16];          // sig_coeff ctx for 4x4 TUs                     (HEVCe.c:1093)
+    u8 grp[32];            // last-position group index                     (HEVCe.c:1047)
+    u8 gmin[12];           // first position of a group                     (HEVCe.c:1048)
+};
+
+inline void fill_tables(Tables& t) {
+    static const u8 LPS[64][4] = {
+        {128, 176, 208, 240}, {128, 167, 197, 227}, {128, 158, 187, 216}, {123, 150, 178, 205}, {116, 142, 169, 195},
+        {111, 135, 160, 185}, {105, 128, 152, 175}, {100, 122, 144, 166}, {95, 116, 137, 158},  {90, 110, 130, 150},
+        {85, 104, 123, 142},  {81, 99, 117, 135},   {77, 94, 111, 128},   {73, 89, 105, 122},   {69, 85, 100, 116},
+        {66, 80, 95, 110},    {62, 76, 90, 104},    {59, 72, 86, 99},     {56, 69, 81, 94},     {53, 65, 77, 89},
+        {51, 62, 73, 85},     {48, 59, 69, 80},     {46, 56, 66, 76},     {43, 53, 63, 72},     {41, 50, 59, 69},
+        {39, 48, 56, 65},     {37, 45, 54, 62},     {35, 43, 51, 59},     {33, 41, 48, 56},     {32, 39, 46, 53},
+        {30, 37, 43, 50},     {29, 35, 41, 48},     {27, 33, 39, 45},     {26, 31, 37, 43},     {24, 30, 35, 41},
+        {23, 28, 33, 39},     {22, 27, 32, 37},     {21, 26, 30, 35},     {20, 24, 29, 33},     {19, 23, 27, 31},
+        {18, 22, 26, 30},     {17, 21, 25, 28},     {16, 20, 23, 27},     {15, 19, 22, 25},     {14, 18, 21, 24},
+        {14, 17, 20, 23},     {13, 16, 19, 22},     {12, 15, 18, 21},     {12, 14, 17, 20},     {11, 14, 16, 19},
+        {11, 13, 15, 18},     {10, 12, 15, 17},     {10, 12, 14, 16},     {9, 11, 13, 15},      {9, 11, 12, 14},
+        {8, 10, 12, 14},      {8, 9, 11, 13},       {7, 9, 11, 12},       {7, 9, 10, 12},       {7, 8, 10, 11},
+        {6, 8, 9, 11},        {6, 7, 9, 10},        {6, 7, 8, 9},         {2, 2, 2, 2}};
+    static const u8 TRANS_LPS[64] = {0,  0,  1,  2,  2,  4,  4,  5,  6,  7,  8,  9,  9,  11, 11, 12, 13, 13, 15, 15, 16, 16,
+                                     18, 18, 19, 19, 21, 21, 22, 22, 23, 24, 24, 25, 26, 26, 27, 27, 28, 29, 29, 30, 30, 30,
+                                     31, 32, 32, 33, 33, 33, 34, 34, 35, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 63};
+    static const u8 HEAD[16] = {139, 141, 157, 184, 184, 63, 153, 138, 138, 111, 141, 94, 138, 182, 154, 154};
+    static const u8 LAST[25] = {110, 110, 124, 0, 0, 125, 140, 153, 0, 0, 125, 127, 140, 109, 0, 111, 143, 127, 111, 79, 108, 123, 63, 154, 0};
+    static const u8 SIG[44] = {111, 111, 125, 110, 110, 94, 124, 108, 124, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125, 107,
+                               125, 141, 179, 153, 125, 141, 140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111, 111};
+    static const u8 ONE[24] = {140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197};
+    static const u8 ABSV[6] = {138, 153, 136, 167, 152, 152};
+    static const u8 P4[16] = {0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8};
+    static const u8 GMIN[12] = {0, 1, 2, 3, 4, 6, 8, 12, 16, 24, 0, 0};
+    for (int s = 0; s < 64; s++)
+        for (int r = 0; r < 4; r++) t.lps[s * 4 + r] = LPS[s][r];
+    for (int s = 0; s < 64; s++)
+        for (int m = 0; m < 2; m++) t.next_lps[(s << 1) | m] = (u8)((TRANS_LPS[s] << 1) | (s == 0 ? !m : m));
+    for (int i = 0; i < 144; i++) t.ctx_iv[i] = 154;
+    for (int i = 0; i < 16; i++) t.ctx_iv[i] = HEAD[i];
+    for (int i = 0; i < 25; i++) t.ctx_iv[CX_LASTX + i] = t.ctx_iv[CX_LASTY + i] = LAST[i];
+    t.ctx_iv[CX_SIGCG] = 91;
+    t.ctx_iv[CX_SIGCG + 1] = 171;
+    for (int i = 0; i < 44; i++) t.ctx_iv[CX_SIG + i] = SIG[i];
+    for (int i = 0; i < 24; i++) t.ctx_iv[CX_ONE + i] = ONE[i];
+    for (int i = 0; i < 6; i++) t.ctx_iv[CX_ABS + i] = ABSV[i];
+    // scans: up-right diagonal / raster / column-major, same pattern inside a CG and over the CG grid (HEVCe.c:1128-1132)
+    for (int type = 0; type < 3; type++) {
+        int n = 0;
+        if (type == 1) { for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) t.scan4[type][n++] = (u8)((y << 2) | x); }
+        else if (type == 2) { for (int x = 0; x < 4; x++) for (int y = 0; y < 4; y++) t.scan4[type][n++] = (u8)((y << 2) | x); }
+        else for (int d = 0; d < 7; d++) for (int y = d < 3 ? d : 3; y >= 0; y--) { int x = d - y; if (x < 4) t.scan4[type][n++] = (u8)((y << 2) | x); }
+    }
+    for (int g = 0; g < 3; g++) {
+        int ncg = 2 << g, n = 0;
+        for (int i = 0; i < 64; i++) t.cgdiag[g][i] = 0;
+        for (int d = 0; d < 2 * ncg - 1; d++)
+            for (int y = d < ncg - 1 ? d : ncg - 1; y >= 0; y--) { int x = d - y; if (x < ncg) t.cgdiag[g][n++] = (u8)((y << 3) | x); }
+    }
+    for (int i = 0; i < 16; i++) t.sigp4[i] = P4[i];
+    for (int i = 0; i < 32; i++) t.grp[i] = (u8)(i < 4 ? i : i < 6 ? 4 : i < 8 ? 5 : i < 12 ? 6 : i < 16 ? 7 : i < 24 ? 8 : 9);
+    for (int i = 0; i < 12; i++) t.gmin[i] = GMIN[i];
+}
+
+// context initialisation for QP = 6*qpd6+4 (HEVCe.c:727-735)
+HEVCE_HD inline u8 ctx_init_value(int iv, int q) {
+    int qp = 6 * q + 4;
+    int st = iclip(((((iv >> 4) * 5 - 45) * qp) >> 4) + ((iv & 15) << 3) - 16, 1, 126);
+    return (u8)(st >= 64 ? ((st - 64) << 1) | 1 : (63 - st) << 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// RD cost (HEVCe.c:177-185) -- saturating
+// ------------------------------------------------------------------------------------------------------------
+struct RdK { int wd, wb, ld, lb; };   // weights and the saturation limits IMAX/weight, fixed per picture
+HEVCE_HD inline RdK rd_consts(int q) {
+    RdK k;
+    k.wd = q < 3 ? 11 : q == 3 ? 5 : 1;
+    k.wb = q == 0 ? 1 : q == 1 ? 4 : q == 2 ? 16 : q == 3 ? 29 : 23;
+    k.ld = q < 3 ? IMAX / 11 : q == 3 ? IMAX / 5 : IMAX;
+    k.lb = q == 0 ? IMAX : q == 1 ? IMAX / 4 : q == 2 ? IMAX / 16 : q == 3 ? IMAX / 29 : IMAX / 23;
+    return k;
+}
+HEVCE_HD inline int rd_cost(const RdK& k, int dist, int bits) {
+    const int c1 = (k.ld <= dist) ? IMAX : k.wd * dist;
+    const int c2 = (k.lb <= bits) ? IMAX : k.wb * bits;
+    return (IMAX - c1 <= c2) ? IMAX : c1 + c2;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// arithmetic coder (HEVCe.c:797-933).  The trial variant (EMIT=false) keeps the full integer state -- including
+// the emulation-prevention bookkeeping that can change the byte count -- but stores no bytes.
+// ------------------------------------------------------------------------------------------------------------
+struct Coder { int range, low, nbits, nbytes, held, z, n; };
+
+HEVCE_HD inline void coder_reset(Coder& c) { c.range = 510; c.low = 0; c.nbits = 23; c.nbytes = 0; c.held = 0xff; c.z = 0; c.n = 0; }
+HEVCE_HD inline int coder_len(const Coder& c) { return 8 * (c.n + c.nbytes) + 23 - c.nbits; }   // HEVCe.c:835
+HEVCE_HD inline bool coder_equal(const Coder& a, const Coder& b) {
+    return a.range == b.range && a.low == b.low && a.nbits == b.nbits && a.nbytes == b.nbytes && a.held == b.held && a.z == b.z && a.n == b.n;
+}
+
+template <bool EMIT>
+struct Bac {
+    Coder c;
+    u8* out;            // EMIT only: destination of this CTU's bytes
+    int cap;            // EMIT only: bytes available at out
+    const Tables* tb;
+
+    HEVCE_HD void emit(int byte) {   // HEVCe.c:821-832
+        const int b = byte & 0xff;
+        if (c.z >= 2 && b <= 3) {
+            if (EMIT) { if (c.n < cap) out[c.n] = 3; }
+            c.n++;
+            c.z = 0;
+        }
+        if (EMIT) { if (c.n < cap) out[c.n] = (u8)b; }
+        c.n++;
+        c.z = b ? 0 : c.z + 1;
+    }
+    HEVCE_HD void carry_out() {      // HEVCe.c:859-879
+        if (c.nbits >= 12) return;
+        const int lead = c.low >> (24 - c.nbits);
+        c.nbits += 8;
+        c.low &= (int)(0xFFFFFFFFu >> c.nbits);
+        if (lead == 0xff) c.nbytes++;
+        else if (c.nbytes > 0) {
+            const int carry = lead >> 8;
+            emit(c.held + carry);
+            c.held = lead & 0xff;
+            for (; c.nbytes > 1; c.nbytes--) emit((0xff + carry) & 0xff);
+        } else { c.nbytes = 1; c.held = lead; }
+    }
+    HEVCE_HD void put_bin(int bin, u8& cx) {   // HEVCe.c:914-933
+        const int v = cx;
+        const int lps = tb->lps[(v >> 1) * 4 + ((c.range >> 6) & 3)];
+        c.range -= lps;
+        if ((bin != 0) != (v & 1)) {
+            const int nb = lps < 8 ? 6 : 9 - bitlen((unsigned)lps);   // renorm table, HEVCe.c:715
+            cx = tb->next_lps[v];
+            c.low = (int)((unsigned)(c.low + c.range) << nb);
+            c.range = lps << nb;
+            c.nbits -= nb;
+        } else {
+            cx = (u8)(v < 124 ? v + 2 : v);                            // HEVCe.c:701
+            if (c.range < 256) { c.low = (int)((unsigned)c.low << 1); c.range <<= 1; c.nbits--; }
+        }
+        carry_out();
+    }
+    HEVCE_HD void put_bypass(int bins, int len) {   // HEVCe.c:899-911
+        bins &= (1 << len) - 1;
+        while (len > 0) {
+            const int n = imin(len, 8);
+            len -= n;
+            const int chunk = (bins >> len) & ((1 << n) - 1);
+            c.low = (int)(((unsigned)c.low << n) + (unsigned)(c.range * chunk));
+            c.nbits -= n;
+            carry_out();
+        }
+    }
+    HEVCE_HD void put_terminate(int bin) {   // HEVCe.c:882-896
+        c.range -= 2;
+        if (bin) { c.low = (int)((unsigned)(c.low + c.range) << 7); c.range = 256; c.nbits -= 7; }
+        else if (c.range < 256) { c.low = (int)((unsigned)c.low << 1); c.range <<= 1; c.nbits--; }
+        carry_out();
+    }
+    HEVCE_HD void finish() {   // HEVCe.c:840-856
+        int fill = 0;
+        if ((c.low >> (32 - c.nbits)) > 0) { emit(c.held + 1); c.low -= 1 << (32 - c.nbits); }
+        else { if (c.nbytes > 0) emit(c.held); fill = 0xff; }
+        for (; c.nbytes > 1; c.nbytes--) emit(fill);
+        const int t = (c.low >> 8) << c.nbits;
+        emit(t >> 16); emit(t >> 8); emit(t);
+    }
+};
+
+// context-set accessors: plain array, or the lane-private word-interleaved layout in shared memory
+struct CtxFlat {
+    u8* p;
+    HEVCE_HD u8& operator[](int k) const { return p[k]; }
+};
+struct CtxLane {   // byte k of lane l lives in word (k>>2)*NL + l  -> every lane owns one bank
+    u8* p;         // = (u8*)lane_ctx + 4*lane
+    HEVCE_HD u8& operator[](int k) const { return p[(k >> 2) * (NL * 4) + (k & 3)]; }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// syntax elements (HEVCe.c:943-1340)
+// ------------------------------------------------------------------------------------------------------------
+HEVCE_HD inline void mpm_list(int l, int a, int (&m)[3]) {   // HEVCe.c:958-977
+    if (l != a) { m[0] = l; m[1] = a; m[2] = (l != 0 && a != 0) ? 0 : (l + a < 2) ? 26 : 1; }
+    else if (l > 1) { m[0] = l; m[1] = ((l + 29) % 32) + 2; m[2] = ((l - 1) % 32) + 2; }
+    else { m[0] = 0; m[1] = 1; m[2] = 26; }
+}
+
+template <bool E, class CX>
+HEVCE_HD inline void put_luma_modes(Bac<E>& b, const CX& cx, int n, const int* pm, const int* pl, const int* pa) {   // HEVCe.c:985-1018
+    int hit[4], mp[4][3];
+    for (int i = 0; i < n; i++) {
+        mpm_list(pl[i], pa[i], mp[i]);
+        hit[i] = -1;
+        for (int j = 0; j < 3; j++) if (mp[i][j] == pm[i]) hit[i] = j;
+        b.put_bin(hit[i] >= 0, cx[CX_YPM]);
+    }
+    for (int i = 0; i < n; i++) {
+        if (hit[i] >= 0) {
+            b.put_bypass(hit[i] > 0, 1);
+            if (hit[i] > 0) b.put_bypass(hit[i] - 1, 1);
+        } else {
+            int r = pm[i];
+            const int hi = imax(mp[i][0], imax(mp[i][1], mp[i][2])), lo = imin(mp[i][0], imin(mp[i][1], mp[i][2]));
+            const int mid = mp[i][0] + mp[i][1] + mp[i][2] - hi - lo;
+            if (r > hi) r--;
+            if (r > mid) r--;
+            if (r > lo) r--;
+            b.put_bypass(r, 5);
+        }
+    }
+}
+
+HEVCE_HD inline int scan_type(int s, int m) {   // HEVCe.c:1134-1150
+    if (s <= 8) { if (iabs(m - 26) <= 4) return 1; if (iabs(m - 10) <= 4) return 2; }
+    return 0;
+}
+
+// scan index -> (y<<5)|x for a TU with lg = log2(size), scan type st
+HEVCE_HD inline int scan_pos(const Tables* tb, int lg, int st, int i) {
+    const int k = tb->scan4[st][i & 15], g = i >> 4;
+    int cy, cx;
+    if (lg == 2) { cy = 0; cx = 0; }
+    else if (st == 1) { cy = g >> 1; cx = g & 1; }      // only 8x8 TUs use the non-diagonal scans
+    else if (st == 2) { cy = g & 1; cx = g >> 1; }
+    else { const int v = tb->cgdiag[lg - 3][g]; cy = v >> 3; cx = v & 7; }
+    return ((cy * 4 + (k >> 2)) << 5) | (cx * 4 + (k & 3));
+}
+
+template <bool E, class CX>
+HEVCE_HD inline void put_last_xy(Bac<E>& b, const CX& cx, int s, int st, int y, int x) {   // HEVCe.c:1046-1087
+    const Tables* tb = b.tb;
+    const int row = ilog2(s) - 2, sh = s > 4;
+    int ty = st == 2 ? x : y, tx = st == 2 ? y : x;
+    const int gy = tb->grp[ty], gx = tb->grp[tx], gmax = tb->grp[s - 1];
+    const int bx = CX_LASTX + 5 * row, by = CX_LASTY + 5 * row;
+    for (int i = 0; i < gx; i++) b.put_bin(1, cx[bx + (i >> sh)]);
+    if (gx < gmax) b.put_bin(0, cx[bx + (gx >> sh)]);
+    for (int i = 0; i < gy; i++) b.put_bin(1, cx[by + (i >> sh)]);
+    if (gy < gmax) b.put_bin(0, cx[by + (gy >> sh)]);
+    if (gx > 3) { tx -= tb->gmin[gx]; for (int i = ((gx - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((tx >> i) & 1, 1); }
+    if (gy > 3) { ty -= tb->gmin[gy]; for (int i = ((gy - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((ty >> i) & 1, 1); }
+}
+
+HEVCE_HD inline int sig_ctx_index(const Tables* tb, int s, int st, int y, int x, int pat) {   // HEVCe.c:1092-1122, luma
+    if (!y && !x) return 0;
+    if (s == 4) return tb->sigp4[y * 4 + x];
+    int k = 9;
+    if (s >= 16) k += 12;
+    if (s == 8 && st) k += 6;
+    if ((y >> 2) || (x >> 2)) k += 3;
+    const int py = y & 3, px = x & 3;
+    int t;
+    if (pat == 0) t = py + px;
+    else if (pat == 1) t = 2 * py;
+    else if (pat == 2) t = 2 * px;
+    else return k + 2;
+    return k + (t == 0 ? 2 : t < 3 ? 1 : 0);
+}
+
+template <bool E>
+HEVCE_HD inline void put_remaining(Bac<E>& b, int v, int rp) {   // HEVCe.c:1154-1169
+    if (v < (3 << rp)) {
+        const int n = v >> rp;
+        b.put_bypass((1 << (n + 1)) - 2, n + 1);
+        b.put_bypass(v & ((1 << rp) - 1), rp);
+    } else {
+        int n = rp;
+        v -= 3 << rp;
+        for (; v >= (1 << n); n++) v -= 1 << n;
+        const int pre = 4 + n - rp;
+        b.put_bypass((1 << pre) - 2, pre);
+        b.put_bypass(v, n);
+    }
+}
+
+// residual_coding() of one TU (HEVCe.c:1173-1269).  lev(y,x) returns the quantised level.
+template <bool E, class CX, class LEV>
+HEVCE_HD inline void put_residual(Bac<E>& b, const CX& cx, int s, int m, const LEV& lev) {
+    const Tables* tb = b.tb;
+    const int st = scan_type(s, m), lg = ilog2(s), ncg = s >> 2;
+    unsigned long long cgsig = 0;
+    int last = 0;
+    for (int i = 0; i < s * s; i++) {
+        const int p = scan_pos(tb, lg, st, i), y = p >> 5, x = p & 31;
+        if (lev(y, x) != 0) { cgsig |= 1ull << ((y >> 2) * 8 + (x >> 2)); last = i; }
+    }
+    {
+        const int p = scan_pos(tb, lg, st, last);
+        put_last_xy(b, cx, s, st, p >> 5, p & 31);
+    }
+    int nz = 0, signs = 0, pat = 0, c1 = 1;
+    int absv[16];
+    for (int i = last; i >= 0; i--) {
+        const int p = scan_pos(tb, lg, st, i), y = p >> 5, x = p & 31, gy = y >> 2, gx = x >> 2;
+        const int v = lev(y, x);
+        const int cg_on = (int)((cgsig >> (gy * 8 + gx)) & 1), first_cg = !gy && !gx;
+        const int k0 = (i & 15) == 0, kend = (i & 15) == 15 || i == last;
+        if (kend) {
+            const int r = gx < ncg - 1 && ((cgsig >> (gy * 8 + gx + 1)) & 1);
+            const int d = gy < ncg - 1 && ((cgsig >> ((gy + 1) * 8 + gx)) & 1);
+            pat = (d << 1) | r;
+            nz = 0;
+            signs = 0;
+            if (!first_cg && i != last) b.put_bin(cg_on, cx[CX_SIGCG + (pat != 0)]);
+        }
+        if (i != last && (first_cg || (cg_on && (!k0 || nz > 0))))
+            b.put_bin(v != 0, cx[CX_SIG + sig_ctx_index(tb, s, st, y, x, pat)]);
+        if (v) { absv[nz++] = iabs(v); signs = (signs << 1) | (v < 0); }
+        if (k0 && nz > 0) {
+            const int set = (first_cg ? 0 : 2) + (c1 == 0);
+            int esc = nz > 8, g2 = -1;
+            c1 = 1;
+            for (int j = 0; j < 8 && j < nz; j++) {
+                const int big = absv[j] > 1;
+                b.put_bin(big, cx[CX_ONE + 4 * set + c1]);
+                if (big) { c1 = 0; if (g2 < 0) g2 = absv[j] > 2; else esc = 1; }
+                else if (c1 > 0 && c1 < 3) c1++;
+            }
+            if (c1 == 0 && g2 >= 0) { b.put_bin(g2, cx[CX_ABS + set]); esc |= g2; }
+            b.put_bypass(signs, nz);
+            if (esc) {
+                int base = 3, rp = 0;
+                for (int j = 0; j < nz; j++) {
+                    const int ev = absv[j] - (j < 8 ? base : 1);
+                    if (ev >= 0) { put_remaining(b, ev, rp); if (absv[j] > (3 << rp)) rp = imin(rp + 1, 4); }
+                    if (absv[j] >= 2) base = 2;
+                }
+            }
+        }
+    }
+}
+
+// One CU (HEVCe.c:1272-1340).  kind 0: 2Nx2N one TU, 1: 2Nx2N four TUs, 2: NxN.  cbf bit k set = TU k has levels.
+// lev4(k, y, x): level of TU k (k = 0 for kind 0).
+template <bool E, class CX, class LEV4>
+HEVCE_HD inline void put_cu(Bac<E>& b, const CX& cx, int s, int kind, const int* pm, const int* pl, const int* pa, int cbf, const LEV4& lev4) {
+    if (s == 8) b.put_bin(kind != 2, cx[CX_PART]);
+    put_luma_modes(b, cx, kind == 2 ? 4 : 1, pm, pl, pa);
+    b.put_bin(0, cx[CX_UVPM]);
+    if (kind != 2) b.put_bin(kind == 1, cx[CX_SPLIT_TU + (s == 32 ? 0 : s == 16 ? 1 : 2)]);
+    b.put_bin(0, cx[CX_UVCBF]);
+    b.put_bin(0, cx[CX_UVCBF]);
+    if (kind == 0) {
+        b.put_bin(cbf & 1, cx[CX_YCBF + 1]);
+        if (cbf & 1) put_residual(b, cx, s, pm[0], [&](int y, int x) { return lev4(0, y, x); });
+    } else {
+        for (int k = 0; k < 4; k++) {
+            const int on = (cbf >> k) & 1;
+            b.put_bin(on, cx[CX_YCBF]);
+            if (on) put_residual(b, cx, s >> 1, pm[kind == 2 ? k : 0], [&](int y, int x) { return lev4(k, y, x); });
+        }
+    }
+}
+
+template <bool E, class CX>
+HEVCE_HD inline void put_split_cu(Bac<E>& b, const CX& cx, int s, int flag, int gtL, int gtA) {   // HEVCe.c:943-947
+    if (s >= 16) b.put_bin(flag, cx[CX_SPLIT_CU + (gtL != 0) + (gtA != 0)]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// transforms
+// ------------------------------------------------------------------------------------------------------------
+#include "hevce_xform_gen.h"
+
+template <int T> struct Xf;
+template <> struct Xf<4>  { static HEVCE_HD void f(const int (&x)[4], int (&y)[4]) { fdst4(x, y); }   static HEVCE_HD void i(const int (&x)[4], int (&y)[4]) { idst4(x, y); } };
+template <> struct Xf<8>  { static HEVCE_HD void f(const int (&x)[8], int (&y)[8]) { fdct8(x, y); }   static HEVCE_HD void i(const int (&x)[8], int (&y)[8]) { idct8(x, y); } };
+template <> struct Xf<16> { static HEVCE_HD void f(const int (&x)[16], int (&y)[16]) { fdct16(x, y); } static HEVCE_HD void i(const int (&x)[16], int (&y)[16]) { idct16(x, y); } };
+template <> struct Xf<32> { static HEVCE_HD void f(const int (&x)[32], int (&y)[32]) { fdct32(x, y); } static HEVCE_HD void i(const int (&x)[32], int (&y)[32]) { idct32(x, y); } };
+
+// ------------------------------------------------------------------------------------------------------------
+// lane-private scratch in global memory, interleaved by lane: element i of lane l at [i*NL + l]
+// ------------------------------------------------------------------------------------------------------------
+struct LaneMem {
+    s16* W;   // working block: residual -> coefficients -> dequantised -> residual'
+    s16* L;   // quantised levels (TU-local raster; four-TU candidates: block k at k*T*T)
+    u8* P;    // prediction
+    u8* R;    // reconstruction, CU-local raster
+    HEVCE_HD s16& w(int i) const { return W[i * NL]; }
+    HEVCE_HD s16& l(int i) const { return L[i * NL]; }
+    HEVCE_HD u8& p(int i) const { return P[i * NL]; }
+    HEVCE_HD u8& r(int i) const { return R[i * NL]; }
+};
+
+HEVCE_HD inline int use_filtered(int s, int m) {   // HEVCe.c:274-280 (HEVC intraHorVerDistThres rule)
+    if (s == 4 || m == 1) return 0;
+    if (m == 0) return 1;
+    const int d = imin(iabs(m - 10), iabs(m - 26));
+    return d > (s == 8 ? 7 : s == 16 ? 1 : 0);
+}
+
+HEVCE_HD inline int intra_angle(int m) {   // HEVCe.c:282
+    const int k = m < 18 ? m - 10 : m - 26;   // signed distance to pure HOR / VER
+    const int a = iabs(k);
+    const int v = a == 0 ? 0 : a == 1 ? 2 : a == 2 ? 5 : a == 3 ? 9 : a == 4 ? 13 : a == 5 ? 17 : a == 6 ? 21 : a == 7 ? 26 : 32;
+    return (m < 18) ? (k < 0 ? v : -v) : (k < 0 ? -v : v);
+}
+
+// One TU of one candidate: reference samples (HEVCe.c:196-257), prediction (:262-381), residual, forward
+// transform (:497-516), RDOQ (:540-595), dequantisation (:600-615), inverse transform, reconstruction, SSE.
+//   rc(y,x)  : reconstructed neighbour sample relative to the TU origin (y or x may be -1, up to 2T-1)
+//   org      : original samples of the TU, pitch CTU
+//   loff     : where this TU's levels go in lm.L ; (ry,rx,rp): where its reconstruction goes in lm.R
+// returns SSE; *nonzero = any level != 0.
+template <int T, class RC>
+HEVCE_HD inline int tu_pipeline(int q, const RdK& rk, int m, int aL, int aLB, int aA, int aAR, const RC& rc, const u8* org,
+                                const LaneMem& lm, int loff, int ry, int rx, int rp, int* nonzero) {
+    constexpr int LG = T == 4 ? 2 : T == 8 ? 3 : T == 16 ? 4 : 5;
+    // ---- reference samples
+    u8 lft[2 * T], top[2 * T];
+    int cor;
+    if (aL && aA) cor = rc(-1, -1);
+    else if (aL) cor = rc(0, -1);
+    else if (aA) cor = rc(-1, 0);
+    else cor = 128;
+    for (int i = 0; i < T; i++) lft[i] = (u8)(aL ? rc(i, -1) : cor);
+    for (int i = T; i < 2 * T; i++) lft[i] = (u8)(aLB ? rc(i, -1) : lft[T - 1]);
+    for (int i = 0; i < T; i++) top[i] = (u8)(aA ? rc(-1, i) : cor);
+    for (int i = T; i < 2 * T; i++) top[i] = (u8)(aAR ? rc(-1, i) : top[T - 1]);
+    if (use_filtered(T, m)) {
+        const int fc = (2 + lft[0] + top[0] + 2 * cor) >> 2;
+        int pl = cor, pt = cor;
+        for (int i = 0; i < 2 * T - 1; i++) {
+            const int cl = lft[i], ct = top[i];
+            lft[i] = (u8)((2 + 2 * cl + pl + lft[i + 1]) >> 2);
+            top[i] = (u8)((2 + 2 * ct + pt + top[i + 1]) >> 2);
+            pl = cl;
+            pt = ct;
+        }
+        cor = fc;
+    }
+    // ---- prediction -> lm.P, residual -> lm.W
+    const bool edge = T <= 16;
+    if (m == 0) {
+        for (int y = 0; y < T; y++)
+            for (int x = 0; x < T; x++)
+                lm.p(y * T + x) = (u8)((T + (T - 1 - x) * lft[y] + (x + 1) * top[T] + (T - 1 - y) * top[x] + (y + 1) * lft[T]) >> (LG + 1));
+    } else if (m == 1) {
+        int dc = T;
+        for (int i = 0; i < T; i++) dc += lft[i] + top[i];
+        dc >>= LG + 1;
+        for (int i = 0; i < T * T; i++) lm.p(i) = (u8)dc;
+        if (edge) {
+            lm.p(0) = (u8)((2 + 2 * dc + lft[0] + top[0]) >> 2);
+            for (int i = 1; i < T; i++) {
+                lm.p(i) = (u8)((2 + 3 * dc + top[i]) >> 2);
+                lm.p(i * T) = (u8)((2 + 3 * dc + lft[i]) >> 2);
+            }
+        }
+    } else if (m == 10) {
+        for (int y = 0; y < T; y++)
+            for (int x = 0; x < T; x++) lm.p(y * T + x) = lft[y];
+        if (edge)
+            for (int x = 0; x < T; x++) lm.p(x) = (u8)iclip(((top[x] - cor) >> 1) + lft[0], 0, 255);
+    } else if (m == 26) {
+        for (int y = 0; y < T; y++)
+            for (int x = 0; x < T; x++) lm.p(y * T + x) = top[x];
+        if (edge)
+            for (int y = 0; y < T; y++) lm.p(y * T) = (u8)iclip(((lft[y] - cor) >> 1) + top[0], 0, 255);
+    } else {
+        const bool horiz = m < 18;
+        const int ang = intra_angle(m), aa = iabs(ang), inv = (8192 + aa / 2) / aa;   // HEVCe.c:283
+        const u8* mainb = horiz ? lft : top;
+        const u8* side = horiz ? top : lft;
+        u8 rf[3 * T + 4];
+        u8* r = rf + T;
+        r[0] = (u8)cor;
+        for (int i = 0; i < 2 * T; i++) r[1 + i] = mainb[i];
+        r[2 * T + 1] = 0;   // read with weight 0 by modes 2 / 34 (HEVCe.c:371-373)
+        const int lastneg = (T * ang) >> 5;
+        for (int i = -1; i > lastneg; i--) r[i] = side[((128 - inv * i) >> 8) - 1];
+        for (int i = 0; i < T; i++) {
+            const int off = ang * (i + 1), oi = off >> 5, of = off & 31;
+            for (int j = 0; j < T; j++) {
+                const u8 pv = (u8)(((32 - of) * r[oi + j + 1] + of * r[oi + j + 2] + 16) >> 5);
+                if (horiz) lm.p(j * T + i) = pv; else lm.p(i * T + j) = pv;
+            }
+        }
+    }
+    for (int y = 0; y < T; y++)
+        for (int x = 0; x < T; x++) lm.w(y * T + x) = (s16)((int)org[y * CTU + x] - lm.p(y * T + x));
+    // ---- forward transform: columns (>> a), rows (>> a+7)
+    {
+        constexpr int A1 = LG - 1, A2 = LG + 6;
+        int v[T], o[T];
+        for (int x = 0; x < T; x++) {
+            for (int y = 0; y < T; y++) v[y] = lm.w(y * T + x);
+            Xf<T>::f(v, o);
+            for (int k = 0; k < T; k++) lm.w(k * T + x) = (s16)((o[k] + (1 << A1 >> 1)) >> A1);
+        }
+        for (int y = 0; y < T; y++) {
+            for (int x = 0; x < T; x++) v[x] = lm.w(y * T + x);
+            Xf<T>::f(v, o);
+            for (int k = 0; k < T; k++) lm.w(y * T + k) = (s16)((o[k] + (1 << A2 >> 1)) >> A2);
+        }
+    }
+    // ---- RDOQ + dequantisation, one 4x4 coefficient group at a time
+    int any = 0;
+    {
+        const int dsh = 10 - LG, sh = 21 - LG + q, add = 1 << sh >> 1, thr = 9 << sh >> 2, qs = 7 - LG + q;
+        for (int cy = 0; cy < T; cy += 4)
+            for (int cx = 0; cx < T; cx += 4) {
+                int lv[16], sum = 0, nzg = 0;
+                for (int k = 0; k < 16; k++) {
+                    const int c = lm.w((cy + (k >> 2)) * T + cx + (k & 3));
+                    const int dl = iabs(c) << 14;                    // |c| <= 32640, no clamp can trigger (HEVCe.c:566)
+                    int lvl = iclip((dl + add) >> sh, -32768, 32767);
+                    const int lo = imax(0, lvl - 2);
+                    int best = IMAX, pick = 0;
+                    for (; lvl >= lo; lvl--) {
+                        const int d1 = iabs(dl - (lvl << sh)) >> dsh;
+                        const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
+                        int rate;                                    // HEVCe.c:526-535
+                        if (lvl < 6) rate = lvl == 0 ? 0 : lvl == 1 ? 70000 : lvl == 2 ? 90000 : lvl == 3 ? 92000 : lvl == 4 ? 157536 : 190304;
+                        else rate = 92000 + ((4 + 2 * (bitlen((unsigned)(lvl - 5)) - 1)) << 15);
+                        const int cost = rd_cost(rk, d, rate);
+                        if (cost < best) { best = cost; pick = lvl; }
+                    }
+                    lv[k] = c < 0 ? -pick : pick;
+                    nzg |= pick;
+                    sum += imin(dl, thr);
+                }
+                if (sum < thr) nzg = 0;
+                any |= nzg;
+                for (int k = 0; k < 16; k++) {
+                    const int idx = (cy + (k >> 2)) * T + cx + (k & 3);
+                    const int l = nzg ? lv[k] : 0;
+                    lm.l(loff + idx) = (s16)l;
+                    lm.w(idx) = (s16)iclip(l * (1 << qs), -32768, 32767);
+                }
+            }
+    }
+    *nonzero = any != 0;
+    // ---- inverse transform + reconstruction + SSE
+    int sse = 0;
+    {
+        int v[T], o[T];
+        if (any) {
+            for (int x = 0; x < T; x++) {
+                for (int y = 0; y < T; y++) v[y] = lm.w(y * T + x);
+                Xf<T>::i(v, o);
+                for (int k = 0; k < T; k++) lm.w(k * T + x) = (s16)iclip((o[k] + 64) >> 7, -32768, 32767);
+            }
+        }
+        for (int y = 0; y < T; y++) {
+            if (any) {
+                for (int x = 0; x < T; x++) v[x] = lm.w(y * T + x);
+                Xf<T>::i(v, o);
+            }
+            for (int x = 0; x < T; x++) {
+                const int res = any ? iclip((o[x] + 2048) >> 12, -32768, 32767) : 0;
+                const int rec = iclip(res + lm.p(y * T + x), 0, 255);
+                const int d = (int)org[y * CTU + x] - rec;
+                lm.r((ry + y) * rp + rx + x) = (u8)rec;
+                sse += d * d;
+            }
+        }
+    }
+    return sse;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// picture-level state
+// ------------------------------------------------------------------------------------------------------------
+struct Job {
+    const u8* img;     // source picture (device), stride src_w
+    u8* rcon;          // reconstruction (device), H x W
+    u8* out;           // bitstream (device)
+    int* result;       // [0] = stream length, [1] = error flags
+    int src_h, src_w;  // original size (clamp + stride, HEVCe.c:1622)
+    int H, W;          // clamped + padded size (HEVCe.c:1581-1582)
+    int q;             // qpd6
+    int out_cap;
+};
+
+enum { ERR_OVERFLOW = 1, ERR_COMMIT_MISMATCH = 2 };
+
+struct Scratch {       // per picture slot, global memory
+    s16* W; s16* L; u8* P; u8* R;   // NL * LANE_ELEMS each
+    s16* ctu_lev;                   // CTU*CTU final levels of the current CTU
+    u8* msz_line;                   // CU-size map row of the CTU row above, W/4 entries
+};
+
+struct Shared {
+    Tables tb;
+    u8 ctx0[144];                   // freshly initialised contexts for this picture's qpd6
+    u8 orig[CTU * CTU];
+    u8 win[(CTU + 1) * WP];
+    u8 msz[81], mpm[81];            // [1+uy][1+ux], 4x4 units; row 0 / col 0 = neighbours
+    u8 kind[16];                    // per 8x8 unit: 0 one TU, 1 four TUs, 2 NxN
+    Coder live;  u8 live_ctx[144];
+    Coder snap[3]; u8 snap_ctx[3][144];
+    Coder start; u8 start_ctx[144];
+    Coder nxn_coder; u8 nxn_ctx[144];
+    int cand_cost[NL];
+    Coder cand_coder[NL];
+    int cand_cbf[NL];
+    u32 lane_ctx[CTXW * NL];
+    s16 nxn_lev[4][16];
+    int nxn_pm[4], nxn_cbf, nxn_cost;
+    int part_sse[CTU];
+    int win_item;                   // decision of the current node: -1 keep split, 0..NL-1 lane, NL = NxN
+    int pu_best;
+    int stream_pos;
+    int error;
+};
+
+// work-item phases.  On the GPU a phase is a strided loop over the CTA's threads followed by __syncthreads();
+// in the simulator it is a loop over the items in a permuted order.
+#if defined(__CUDA_ARCH__)
+#define PAR_FOR(item, n) for (int item = (int)threadIdx.x; item < (n); item += (int)blockDim.x)
+#define PHASE_END() __syncthreads()
+#else
+extern int g_sim_order;   // 0 forward, 1 reverse, >=2 multiplicative permutation
+inline int sim_item(int i, int n) {
+    if (g_sim_order == 0 || n <= 1) return i;
+    if (g_sim_order == 1) return n - 1 - i;
+    int a = 2 * g_sim_order + 1;
+    auto gcd = [](int x, int y) { while (y) { int t = x % y; x = y; y = t; } return x; };
+    while (gcd(a, n) != 1) a += 2;
+    return (int)(((long long)i * a + 7) % n);
+}
+#define PAR_FOR(item, n) for (int item##_i = 0, item = 0; item##_i < (n) && ((item = sim_item(item##_i, (n))), true); item##_i++)
+#define PHASE_END() ((void)0)
+#endif
+
+// candidate lanes: thread index -> (step, mode).  Steps: 0 = 2Nx2N one TU, 1 = 2Nx2N four TUs, 2 = NxN PU round.
+// Modes 0..31 of each step share a warp; the three leftover modes of every step are packed behind them.
+HEVCE_HD inline int lane_item(int nsteps, int step, int mode) { return mode < 32 ? step * 32 + mode : nsteps * 32 + step * 3 + (mode - 32); }
+HEVCE_HD inline void lane_decode(int nsteps, int item, int& step, int& mode) {
+    if (item < nsteps * 32) { step = item >> 5; mode = item & 31; }
+    else { const int r = item - nsteps * 32; step = r / 3; mode = 32 + r % 3; }
+}
+
+struct Avail { int L, LB, A, AR; };
+HEVCE_HD inline Avail sub_avail(const Avail& a, int k) {   // HEVCe.c:1376-1379
+    Avail r;
+    r.L = (k & 1) ? 1 : a.L;
+    r.LB = k == 0 ? a.L : k == 2 ? a.LB : 0;
+    r.A = (k & 2) ? 1 : a.A;
+    r.AR = k == 0 ? a.A : k == 1 ? a.AR : k == 2 ? 1 : 0;
+    return r;
+}
+
+HEVCE_HD inline LaneMem lane_mem(const Scratch& sc, int lane) {
+    LaneMem lm;
+    lm.W = sc.W + lane; lm.L = sc.L + lane; lm.P = sc.P + lane; lm.R = sc.R + lane;
+    return lm;
+}
+
+// window sample relative to CTU pixel (y,x); y or x may be -1
+#define HEVCE_WIN(sm, y, x) ((sm).win[(1 + (y)) * WP + 1 + (x)])
+
+// One trial lane of a CU node of size S at CTU position (y0,x0).
+template <int S>
+HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int q, int item, int step, int mode, int y0, int x0, const Avail& av,
+                                int depth, int gtL, int gtA, int pmL, int pmA) {
+    constexpr int H = S / 2;
+    const LaneMem lm = lane_mem(sc, item);
+    const RdK rk = rd_consts(q);
+    const u8* org = sm.orig + y0 * CTU + x0;
+    int sse = 0, cbf = 0;
+    if (step == 0) {
+        int nzf;
+        auto rc = [&](int y, int x) -> int { return HEVCE_WIN(sm, y0 + y, x0 + x); };
+        sse = tu_pipeline<S>(q, rk, mode, av.L, av.LB, av.A, av.AR, rc, org, lm, 0, 0, 0, S, &nzf);
+        cbf = nzf;
+    } else {
+        for (int k = 0; k < 4; k++) {
+            const int oy = (k >> 1) * H, ox = (k & 1) * H;
+            const Avail sa = sub_avail(av, k);
+            int nzf;
+            auto rc = [&](int y, int x) -> int {   // inside the CU: this candidate's own reconstruction
+                const int yy = oy + y, xx = ox + x;
+                if (yy >= 0 && xx >= 0 && yy < S && xx < S) return lm.r(yy * S + xx);
+                return HEVCE_WIN(sm, y0 + yy, x0 + xx);
+            };
+            sse += tu_pipeline<H>(q, rk, mode, sa.L, sa.LB, sa.A, sa.AR, rc, org + oy * CTU + ox, lm, k * H * H, oy, ox, S, &nzf);
+            cbf |= nzf << k;
+        }
+    }
+    // trial entropy coding from the node snapshot
+    Bac<false> b;
+    b.c = sm.snap[depth];
+    b.out = nullptr; b.cap = 0; b.tb = &sm.tb;
+    const CtxLane cx = {(u8*)sm.lane_ctx + 4 * item};
+    for (int k = 0; k < NCTX; k++) cx[k] = sm.snap_ctx[depth][k];
+    put_split_cu(b, cx, S, 0, gtL, gtA);
+    const int ts = step == 0 ? S : H;
+    put_cu(b, cx, S, step, &mode, &pmL, &pmA, cbf, [&](int k, int y, int x) -> int { return lm.l(k * H * H + y * ts + x); });
+    sm.cand_cost[item] = rd_cost(rk, sse, coder_len(b.c) - coder_len(sm.snap[depth]));
+    sm.cand_coder[item] = b.c;
+    sm.cand_cbf[item] = cbf;
+}
+
+// One lane of an NxN PU round (HEVCe.c:1499-1528): 4x4 pipeline + residual coding from a fresh coder.
+HEVCE_HD inline void pu_lane(Shared& sm, const Scratch& sc, int q, int item, int mode, int y0, int x0, const Avail& av, int k) {
+    const LaneMem lm = lane_mem(sc, item);
+    const RdK rk = rd_consts(q);
+    const int oy = (k >> 1) * 4, ox = (k & 1) * 4;
+    const Avail sa = sub_avail(av, k);
+    int nzf;
+    auto rc = [&](int y, int x) -> int { return HEVCE_WIN(sm, y0 + oy + y, x0 + ox + x); };
+    const int sse = tu_pipeline<4>(q, rk, mode, sa.L, sa.LB, sa.A, sa.AR, rc, sm.orig + (y0 + oy) * CTU + x0 + ox, lm, 0, 0, 0, 4, &nzf);
+    Bac<false> b;
+    coder_reset(b.c);
+    b.out = nullptr; b.cap = 0; b.tb = &sm.tb;
+    const CtxLane cx = {(u8*)sm.lane_ctx + 4 * item};
+    for (int i = 0; i < NCTX; i++) cx[i] = sm.ctx0[i];
+    put_residual(b, cx, 4, mode, [&](int y, int x) -> int { return lm.l(y * 4 + x); });
+    sm.cand_cost[item] = rd_cost(rk, sse, coder_len(b.c));
+    sm.cand_cbf[item] = nzf;
+}
+
+// Evaluate the non-split candidates of one CU node and adopt the winner (HEVCe.c:1420-1559).
+// split_cost: RD cost of the already-coded split alternative (IMAX for 8x8 nodes).
+template <int S>
+HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int x0, const Avail& av, int depth) {
+    constexpr int H = S / 2, N4 = S / 4;
+    constexpr int NSTEP = S == 8 ? 3 : 2;
+    const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
+    const int gtL = S > sm.msz[my * 9 + mx - 1], gtA = S > sm.msz[(my - 1) * 9 + mx];
+    const int pmL = sm.mpm[my * 9 + mx - 1], pmA = sm.mpm[(my - 1) * 9 + mx];
+
+    // split alternative: distortion of what the children left in the window (HEVCe.c:1409-1410)
+    if (S > 8) {
+        PAR_FOR(row, S) {
+            int acc = 0;
+            for (int x = 0; x < S; x++) { const int d = (int)sm.orig[(y0 + row) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + row, x0 + x); acc += d * d; }
+            sm.part_sse[row] = acc;
+        }
+        PHASE_END();
+    }
+    // all one-TU / four-TU candidates (+ NxN PU round 0)
+    PAR_FOR(item, NSTEP * NMODE) {
+        int step, mode;
+        lane_decode(NSTEP, item, step, mode);
+        if (step < 2) trial_lane<S>(sm, sc, q, item, step, mode, y0, x0, av, depth, gtL, gtA, pmL, pmA);
+        else pu_lane(sm, sc, q, item, mode, y0, x0, av, 0);
+    }
+    PHASE_END();
+    if (S == 8) {
+        for (int k = 0; k < 4; k++) {
+            if (k > 0) {
+                PAR_FOR(item, NSTEP * NMODE) {
+                    int step, mode;
+                    lane_decode(NSTEP, item, step, mode);
+                    if (step == 2) pu_lane(sm, sc, q, item, mode, y0, x0, av, k);
+                }
+                PHASE_END();
+            }
+            PAR_FOR(one, 1) {   // best PU mode, last minimum wins (HEVCe.c:1521)
+                int best = IMAX, bm = 0;
+                for (int m = 0; m < NMODE; m++) {
+                    const int c = sm.cand_cost[lane_item(NSTEP, 2, m)];
+                    if (best >= c) { best = c; bm = m; }
+                }
+                const int it = lane_item(NSTEP, 2, bm);
+                const LaneMem lm = lane_mem(sc, it);
+                const int oy = (k >> 1) * 4, ox = (k & 1) * 4;
+                sm.nxn_pm[k] = bm;
+                if (k == 0) sm.nxn_cbf = 0;
+                sm.nxn_cbf |= sm.cand_cbf[it] << k;
+                for (int i = 0; i < 16; i++) {
+                    sm.nxn_lev[k][i] = lm.l(i);
+                    HEVCE_WIN(sm, y0 + oy + (i >> 2), x0 + ox + (i & 3)) = lm.r(i);
+                }
+            }
+            PHASE_END();
+        }
+        PAR_FOR(one, 1) {   // the NxN CU as a whole, from the node snapshot (HEVCe.c:1531-1544)
+            Bac<false> b;
+            b.c = sm.snap[depth];
+            b.out = nullptr; b.cap = 0; b.tb = &sm.tb;
+            const CtxFlat cx = {sm.nxn_ctx};
+            for (int i = 0; i < NCTX; i++) cx[i] = sm.snap_ctx[depth][i];
+            int pl[4], pa[4], pm[4];
+            for (int k = 0; k < 4; k++) pm[k] = sm.nxn_pm[k];
+            pl[0] = pmL;   pa[0] = pmA;
+            pl[1] = pm[0]; pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
+            pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; pa[2] = pm[0];
+            pl[3] = pm[2]; pa[3] = pm[1];
+            put_split_cu(b, cx, S, 0, gtL, gtA);
+            put_cu(b, cx, S, 2, pm, pl, pa, sm.nxn_cbf, [&](int k, int y, int x) -> int { return sm.nxn_lev[k][y * 4 + x]; });
+            int sse = 0;
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++) { const int d = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += d * d; }
+            sm.nxn_cost = rd_cost(rd_consts(q), sse, coder_len(b.c) - coder_len(sm.snap[depth]));
+            sm.nxn_coder = b.c;
+        }
+        PHASE_END();
+    }
+    // decision: reference order, every comparison is ">=" so the last minimum wins (HEVCe.c:1440, 1476, 1546)
+    PAR_FOR(one, 1) {
+        int best = IMAX, win = -1;
+        if (S > 8) {
+            int sse = 0;
+            for (int r = 0; r < S; r++) sse += sm.part_sse[r];
+            best = rd_cost(rd_consts(q), sse, coder_len(sm.live) - coder_len(sm.snap[depth]));
+        }
+        for (int step = 0; step < 2; step++)
+            for (int m = 0; m < NMODE; m++) {
+                const int it = lane_item(NSTEP, step, m);
+                if (best >= sm.cand_cost[it]) { best = sm.cand_cost[it]; win = it; }
+            }
+        if (S == 8 && best >= sm.nxn_cost) win = NL;
+        sm.win_item = win;
+    }
+    PHASE_END();
+    const int win = sm.win_item;
+    if (win < 0) return;   // the split stays: live state, window, levels and maps are already the children's
+    // adoption
+    if (win == NL) {
+        PAR_FOR(i, 64) {
+            const int k = i >> 4, j = i & 15, oy = (k >> 1) * 4, ox = (k & 1) * 4;
+            sc.ctu_lev[(y0 + oy + (j >> 2)) * CTU + x0 + ox + (j & 3)] = sm.nxn_lev[k][j];
+        }
+        PAR_FOR(i, NCTX) sm.live_ctx[i] = sm.nxn_ctx[i];
+        PAR_FOR(one, 1) {
+            sm.live = sm.nxn_coder;
+            sm.kind[(y0 >> 3) * 4 + (x0 >> 3)] = (u8)(2 | (sm.nxn_cbf << 4));
+            for (int k = 0; k < 4; k++) {
+                sm.msz[(my + (k >> 1)) * 9 + mx + (k & 1)] = 8;
+                sm.mpm[(my + (k >> 1)) * 9 + mx + (k & 1)] = (u8)sm.nxn_pm[k];
+            }
+        }
+    } else {
+        int step, mode;
+        lane_decode(NSTEP, win, step, mode);
+        const LaneMem lm = lane_mem(sc, win);
+        PAR_FOR(i, S * S) {
+            const int y = i / S, x = i % S;
+            HEVCE_WIN(sm, y0 + y, x0 + x) = lm.r(i);
+            int li;
+            if (step == 0) li = i;
+            else { const int k = (y >= H) * 2 + (x >= H); li = k * H * H + (y % H) * H + (x % H); }
+            sc.ctu_lev[(y0 + y) * CTU + x0 + x] = lm.l(li);
+        }
+        const CtxLane cx = {(u8*)sm.lane_ctx + 4 * win};
+        PAR_FOR(i, NCTX) sm.live_ctx[i] = cx[i];
+        PAR_FOR(i, N4 * N4) {
+            const int idx = (my + i / N4) * 9 + mx + i % N4;
+            sm.msz[idx] = (u8)S;
+            sm.mpm[idx] = (u8)mode;
+        }
+        PAR_FOR(i, (S >= 8 ? (S / 8) * (S / 8) : 1)) {
+            const int n8 = S / 8;
+            sm.kind[((y0 >> 3) + i / n8) * 4 + (x0 >> 3) + i % n8] = (u8)(step | (sm.cand_cbf[win] << 4));
+        }
+        PAR_FOR(one, 1) sm.live = sm.cand_coder[win];
+    }
+    PHASE_END();
+}
+
+// enter a node: snapshot the live state (HEVCe.c:1364-1365) and, for splittable nodes, code split_cu_flag = 1
+template <int S>
+HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
+    PAR_FOR(i, NCTX) sm.snap_ctx[depth][i] = sm.live_ctx[i];
+    PAR_FOR(one, 1) sm.snap[depth] = sm.live;
+    PHASE_END();
+    if (S > 8) {
+        PAR_FOR(one, 1) {
+            const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
+            Bac<false> b;
+            b.c = sm.live; b.out = nullptr; b.cap = 0; b.tb = &sm.tb;
+            const CtxFlat cx = {sm.live_ctx};
+            put_split_cu(b, cx, S, 1, S > sm.msz[my * 9 + mx - 1], S > sm.msz[(my - 1) * 9 + mx]);
+            sm.live = b.c;
+        }
+        PHASE_END();
+    }
+}
+
+// re-encode the decided CTU with the byte-writing coder (replaces the reference's per-trial byte buffers)
+HEVCE_HD inline void commit_cu(Bac<true>& b, const CtxFlat& cx, const Shared& sm, const s16* lev, int s, int y0, int x0) {
+    const int my = 1 + y0 / 4, mx = 1 + x0 / 4, h = s / 2;
+    const int kd = sm.kind[(y0 >> 3) * 4 + (x0 >> 3)], kind = kd & 3, cbf = kd >> 4;
+    int pm[4], pl[4], pa[4];
+    pm[0] = sm.mpm[my * 9 + mx];
+    pl[0] = sm.mpm[my * 9 + mx - 1];
+    pa[0] = sm.mpm[(my - 1) * 9 + mx];
+    if (kind == 2) {
+        pm[1] = sm.mpm[my * 9 + mx + 1]; pm[2] = sm.mpm[(my + 1) * 9 + mx]; pm[3] = sm.mpm[(my + 1) * 9 + mx + 1];
+        pl[1] = pm[0]; pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
+        pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; pa[2] = pm[0];
+        pl[3] = pm[2]; pa[3] = pm[1];
+    }
+    put_cu(b, cx, s, kind, pm, pl, pa, cbf, [&](int k, int y, int x) -> int {
+        const int oy = kind == 0 ? 0 : (k >> 1) * h, ox = kind == 0 ? 0 : (k & 1) * h;
+        return lev[(y0 + oy + y) * CTU + x0 + ox + x];
+    });
+}
+
+HEVCE_HD inline void commit_ctu(Bac<true>& b, const CtxFlat& cx, const Shared& sm, const s16* lev) {
+    auto gt = [&](int s, int y, int x, int dy, int dx) { return s > sm.msz[(1 + y / 4 + dy) * 9 + 1 + x / 4 + dx]; };
+    if (sm.msz[10] == 32) {
+        put_split_cu(b, cx, 32, 0, gt(32, 0, 0, 0, -1), gt(32, 0, 0, -1, 0));
+        commit_cu(b, cx, sm, lev, 32, 0, 0);
+        return;
+    }
+    put_split_cu(b, cx, 32, 1, gt(32, 0, 0, 0, -1), gt(32, 0, 0, -1, 0));
+    for (int a = 0; a < 4; a++) {
+        const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
+        const int sz = sm.msz[(1 + y16 / 4) * 9 + 1 + x16 / 4];
+        put_split_cu(b, cx, 16, sz != 16, gt(16, y16, x16, 0, -1), gt(16, y16, x16, -1, 0));
+        if (sz == 16) { commit_cu(b, cx, sm, lev, 16, y16, x16); continue; }
+        for (int c = 0; c < 4; c++) commit_cu(b, cx, sm, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
+    }
+}
+
+// stream header (HEVCe.c:665-691): constant NAL units with ue(width), ue(height) spliced into the SPS
+HEVCE_HD inline int write_header(u8* out, int q, int H, int W) {
+    const u8 VPS[27] = {0, 0, 1, 0x40, 1, 0x0c, 1, 0xff, 0xff, 3, 0x10, 0, 0, 3, 0, 0, 3, 0, 0, 3, 0, 0, 3, 0, 0xb4, 0xf0, 0x24};
+    const u8 SPS[22] = {0, 0, 1, 0x42, 1, 1, 3, 0x10, 0, 0, 3, 0, 0, 3, 0, 0, 3, 0, 0, 3, 0, 0xb4};
+    const u8 PPS[11] = {0, 0, 1, 0x44, 1, 0xc0, 0x90, 0x91, 0x81, 0xd9, 0x20};
+    const u8 SLICE[6] = {0, 0, 1, 0x26, 1, 0xac};
+    const u8 SQP[5][2] = {{0x16, 0xde}, {0x10, 0xde}, {0x2b, 0x78}, {0x4d, 0xe0}, {0x97, 0x80}};
+    int n = 0;
+    for (int i = 0; i < 27; i++) out[n++] = VPS[i];
+    for (int i = 0; i < 22; i++) out[n++] = SPS[i];
+    // bit writer, MSB first
+    unsigned long long acc = 0;
+    int nb = 0;
+    auto put = [&](unsigned v, int len) {
+        for (int i = len - 1; i >= 0; i--) {
+            acc = (acc << 1) | ((v >> i) & 1);
+            if (++nb == 8) { out[n++] = (u8)acc; acc = 0; nb = 0; }
+        }
+    };
+    auto ue = [&](int v) {   // the reference's ue(v): length derived from v+2 (HEVCe.c:642-648)
+        int len = 1;
+        v++;
+        for (int t = v + 1; t != 1; t >>= 1) len += 2;
+        put((unsigned)(v & ((1 << ((len + 1) >> 1)) - 1)), (len >> 1) + ((len + 1) >> 1));
+    };
+    put(0x0a, 4);
+    ue(W);
+    ue(H);
+    put(0x197ee4, 22);
+    put(0x681ed1, 24);
+    if (nb) { out[n++] = (u8)(acc << (8 - nb)); }
+    for (int i = 0; i < 11; i++) out[n++] = PPS[i];
+    for (int i = 0; i < 6; i++) out[n++] = SLICE[i];
+    out[n++] = SQP[q][0];
+    out[n++] = SQP[q][1];
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// one picture (HEVCe.c:1570-1647)
+// ------------------------------------------------------------------------------------------------------------
+HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared& sm, const Scratch& sc) {
+    const int q = job.q, H = job.H, W = job.W;
+    // tables + initial state
+    PAR_FOR(i, (int)sizeof(Tables)) ((u8*)&sm.tb)[i] = ((const u8*)&tables)[i];
+    PHASE_END();
+    PAR_FOR(i, 144) {
+        const u8 v = i < NCTX ? ctx_init_value(sm.tb.ctx_iv[i], q) : (u8)0;
+        sm.ctx0[i] = v;
+        sm.live_ctx[i] = v;
+    }
+    PAR_FOR(i, 81) { sm.msz[i] = CTU; sm.mpm[i] = 1; }
+    PAR_FOR(i, W / 4) sc.msz_line[i] = CTU;
+    PAR_FOR(one, 1) {
+        coder_reset(sm.live);
+        sm.error = 0;
+        sm.stream_pos = write_header(job.out, q, H, W);
+    }
+    PHASE_END();
+
+    for (int cy = 0; cy < H; cy += CTU) {
+        for (int cx = 0; cx < W; cx += CTU) {
+            const Avail av = {cx > 0, 0, cy > 0, cy > 0 && cx + CTU < W};   // HEVCe.c:1606-1609
+            // ---- load: original (edge-replicated), neighbour samples, neighbour maps
+            PAR_FOR(i, CTU * CTU) {
+                const int y = imin(cy + i / CTU, job.src_h - 1), x = imin(cx + i % CTU, job.src_w - 1);
+                sm.orig[i] = job.img[(size_t)y * job.src_w + x];
+            }
+            PAR_FOR(i, CTU) sm.win[(1 + i) * WP] = cx > 0 ? job.rcon[(size_t)(cy + i) * W + cx - 1] : (u8)0;
+            PAR_FOR(j, 2 * CTU + 1) sm.win[j] = cy > 0 ? job.rcon[(size_t)(cy - 1) * W + iclip(cx - 1 + j, 0, W - 1)] : (u8)0;
+            PAR_FOR(i, 8) {
+                sm.msz[i + 1] = sc.msz_line[cx / 4 + i];                               // above row: CU sizes scroll,
+                sm.mpm[i + 1] = 1;                                                     // modes stay DC (HEVCe.c:1634-1637)
+                sm.msz[(i + 1) * 9] = cx > 0 ? sm.msz[(i + 1) * 9 + 8] : (u8)CTU;      // left column = previous CTU's last column
+                sm.mpm[(i + 1) * 9] = cx > 0 ? sm.mpm[(i + 1) * 9 + 8] : (u8)1;
+            }
+            PAR_FOR(i, NCTX) sm.start_ctx[i] = sm.live_ctx[i];
+            PAR_FOR(one, 1) { sm.live.n = 0; sm.start = sm.live; }
+            PHASE_END();
+
+            // ---- CU quadtree, z-order, children before the parent's own candidates (HEVCe.c:1403-1413)
+            enter_node<32>(sm, 0, 0, 0);
+            for (int a = 0; a < 4; a++) {
+                const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
+                const Avail av16 = sub_avail(av, a);
+                enter_node<16>(sm, y16, x16, 1);
+                for (int c = 0; c < 4; c++) {
+                    const int y8 = y16 + (c >> 1) * 8, x8 = x16 + (c & 1) * 8;
+                    enter_node<8>(sm, y8, x8, 2);
+                    eval_node<8>(sm, sc, q, y8, x8, sub_avail(av16, c), 2);
+                }
+                eval_node<16>(sm, sc, q, y16, x16, av16, 1);
+            }
+            eval_node<32>(sm, sc, q, 0, 0, av, 0);
+
+            // ---- store reconstruction + map row, terminate bin, commit the CTU's bytes
+            PAR_FOR(i, CTU * CTU) job.rcon[(size_t)(cy + i / CTU) * W + cx + i % CTU] = HEVCE_WIN(sm, i / CTU, i % CTU);
+            PAR_FOR(i, 8) sc.msz_line[cx / 4 + i] = sm.msz[8 * 9 + 1 + i];
+            PAR_FOR(one, 1) {
+                const int last = cy + CTU >= H && cx + CTU >= W;
+                Bac<false> t;
+                t.c = sm.live; t.out = nullptr; t.cap = 0; t.tb = &sm.tb;
+                t.put_terminate(last);                                                  // HEVCe.c:1630
+                if (last) t.finish();                                                   // HEVCe.c:1640
+                Bac<true> b;
+                b.c = sm.start; b.tb = &sm.tb;
+                b.out = job.out + sm.stream_pos;
+                b.cap = imax(0, job.out_cap - sm.stream_pos);
+                const CtxFlat cxs = {sm.start_ctx};
+                commit_ctu(b, cxs, sm, sc.ctu_lev);
+                b.put_terminate(last);
+                if (last) b.finish();
+                if (!coder_equal(b.c, t.c)) sm.error |= ERR_COMMIT_MISMATCH;
+                for (int i = 0; i < NCTX; i++) if (sm.start_ctx[i] != sm.live_ctx[i]) sm.error |= ERR_COMMIT_MISMATCH;
+                if (b.c.n > b.cap) sm.error |= ERR_OVERFLOW;
+                sm.stream_pos += b.c.n;
+                sm.live = t.c;
+            }
+            PHASE_END();
+        }
+    }
+    PAR_FOR(one, 1) {
+        job.result[0] = sm.stream_pos;
+        job.result[1] = sm.error;
+    }
+    PHASE_END();
+}
+
+}   // namespace hevce

@@ -1,0 +1,371 @@
+// hevce_cuda.cu -- sm_100a kernels + device-resident sessions of libhevce_b200.so.
+//
+// Kernel: hevce_encode_kernel -- a persistent grid of 128-thread CTAs; every CTA pulls pictures from a queue
+// (largest first) and encodes each one completely (hevce_core.h: encode_picture).  Pictures are independent, so the
+// grid needs no inter-CTA communication; the batch is the parallel axis.
+//
+// Host side here is the thin layer between the plain-C API (hevce_api.c) and the device: buffer management in HBM,
+// pinned staging, launches, CUDA-event timing.  No CPU implementation of any encoder stage exists in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <vector>
+
+#include "../../include/hevce.h"
+#include "hevce_core.h"
+#include "hevce_internal.h"
+
+using namespace hevce;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            fprintf(stderr, "libhevce_b200: %s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return HEVCE_ERR_CUDA;                                                                       \
+        }                                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------------------
+__device__ Tables g_tables;
+
+__global__ void __launch_bounds__(NL, 4)
+hevce_encode_kernel(const Job* __restrict__ jobs, const int* __restrict__ order, int njobs, const Scratch* __restrict__ slots, int* counter) {
+    __shared__ Shared sm;
+    __shared__ int s_next;
+    const Scratch sc = slots[blockIdx.x];
+    for (;;) {
+        if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
+        __syncthreads();
+        const int k = s_next;
+        __syncthreads();
+        if (k >= njobs) break;
+        const Job job = jobs[order[k]];
+        encode_picture(job, g_tables, sm, sc);
+    }
+}
+
+// integer-issue micro-benchmark: 8 independent IMAD chains + 8 independent LOP3/IADD3 chains per thread
+__global__ void __launch_bounds__(256) hevce_int_peak_kernel(int iters, int seed, int* sink) {
+    int a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = seed + i * 7 + threadIdx.x; b[i] = seed * 3 + i + blockIdx.x; }
+    const int m = seed | 1, c = seed + 11;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            a[i] = a[i] * m + c;            // IMAD  (fma pipe)
+            b[i] = (b[i] ^ c) + a[i];       // LOP3 + IADD3 (alu pipe)
+        }
+    }
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r ^= a[i] ^ b[i];
+    if (r == 0x7fffffff) sink[0] = r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-device state
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct DeviceInfo {
+    bool ready = false;
+    int sms = 0, ctas_per_sm = 0;
+};
+std::mutex g_dev_mutex;
+DeviceInfo g_dev[64];
+
+int device_prepare(int device) {
+    std::lock_guard<std::mutex> lk(g_dev_mutex);
+    if (device < 0 || device >= 64) return HEVCE_ERR_ARG;
+    CK(cudaSetDevice(device));
+    if (g_dev[device].ready) return 0;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        fprintf(stderr, "libhevce_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor);
+        return HEVCE_ERR_CUDA;
+    }
+    static Tables host_tables;
+    fill_tables(host_tables);
+    CK(cudaMemcpyToSymbol(g_tables, &host_tables, sizeof(Tables)));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevce_encode_kernel, NL, 0));
+    if (occ < 1) occ = 1;
+    g_dev[device].sms = prop.multiProcessorCount;
+    g_dev[device].ctas_per_sm = occ;
+    g_dev[device].ready = true;
+    return 0;
+}
+
+template <class T>
+int grow(T** p, size_t* cap, size_t need) {   // grow-only device buffer
+    if (need <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 8 + 256;
+    CK(cudaMalloc((void**)p, want * sizeof(T)));
+    *cap = want;
+    return 0;
+}
+
+}   // namespace
+
+struct hevce_session {
+    int device = 0, n = 0, grid = 0, launches = 0;
+    float kernel_ms = 0.f;
+    long long h2d = 0, d2h = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<Job> jobs;
+    std::vector<size_t> img_off, rcon_off, out_off;
+    std::vector<int> order, results;
+    size_t img_total = 0, rcon_total = 0, out_total = 0;
+    // device buffers (grow-only)
+    u8 *d_img = nullptr, *d_rcon = nullptr, *d_out = nullptr;
+    size_t c_img = 0, c_rcon = 0, c_out = 0;
+    Job* d_jobs = nullptr; size_t c_jobs = 0;
+    int* d_order = nullptr; size_t c_order = 0;
+    int* d_results = nullptr; size_t c_results = 0;
+    int* d_counter = nullptr;
+    Scratch* d_slots = nullptr; size_t c_slots = 0;
+    s16 *d_W = nullptr, *d_L = nullptr, *d_lev = nullptr; u8 *d_P = nullptr, *d_R = nullptr, *d_line = nullptr;
+    size_t c_W = 0, c_L = 0, c_lev = 0, c_P = 0, c_R = 0, c_line = 0;
+    int line_pitch = 0;
+    // pinned staging
+    u8* h_stage = nullptr; size_t c_stage = 0;
+};
+
+static int stage_reserve(hevce_session* s, size_t need) {
+    if (need <= s->c_stage) return 0;
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    s->h_stage = nullptr;
+    s->c_stage = 0;
+    CK(cudaHostAlloc((void**)&s->h_stage, need + need / 8 + 4096, cudaHostAllocDefault));
+    s->c_stage = need + need / 8 + 4096;
+    return 0;
+}
+
+extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, const int* xsz, const int* qpd6) {
+    if (!s || n < 0 || (n > 0 && (!ysz || !xsz || !qpd6))) return HEVCE_ERR_ARG;
+    int rc = device_prepare(s->device);
+    if (rc) return rc;
+    const int max_dim = hevce_internal_max_dim();
+    s->n = n;
+    s->jobs.assign(n, Job());
+    s->img_off.assign(n, 0); s->rcon_off.assign(n, 0); s->out_off.assign(n, 0);
+    size_t io = 0, ro = 0, oo = 0;
+    int maxW = CTU;
+    for (int i = 0; i < n; i++) {
+        if (ysz[i] <= 0 || xsz[i] <= 0 || qpd6[i] < 0 || qpd6[i] > 4) return HEVCE_ERR_ARG;
+        Job& j = s->jobs[i];
+        j.src_h = ysz[i]; j.src_w = xsz[i];
+        j.H = (std::min(ysz[i], max_dim) + CTU - 1) / CTU * CTU;     // HEVCe.c:1581-1582
+        j.W = (std::min(xsz[i], max_dim) + CTU - 1) / CTU * CTU;
+        j.q = qpd6[i];
+        j.out_cap = 256 + 2 * j.H * j.W;
+        s->img_off[i] = io; s->rcon_off[i] = ro; s->out_off[i] = oo;
+        // only the rows/columns the encoder can touch are transferred (a picture larger than the clamp is cropped)
+        io += ((size_t)std::min(j.src_h, j.H) * j.src_w + 255) & ~(size_t)255;
+        ro += (size_t)j.H * j.W;
+        oo += ((size_t)j.out_cap + 255) & ~(size_t)255;
+        maxW = std::max(maxW, j.W);
+    }
+    s->img_total = io; s->rcon_total = ro; s->out_total = oo;
+    if (n == 0) return 0;
+    const DeviceInfo& di = g_dev[s->device];
+    s->grid = std::min(n, di.sms * di.ctas_per_sm);
+    if ((rc = grow(&s->d_img, &s->c_img, io))) return rc;
+    if ((rc = grow(&s->d_rcon, &s->c_rcon, ro))) return rc;
+    if ((rc = grow(&s->d_out, &s->c_out, oo))) return rc;
+    if ((rc = grow(&s->d_jobs, &s->c_jobs, (size_t)n))) return rc;
+    if ((rc = grow(&s->d_order, &s->c_order, (size_t)n))) return rc;
+    if ((rc = grow(&s->d_results, &s->c_results, (size_t)2 * n))) return rc;
+    if (!s->d_counter) CK(cudaMalloc((void**)&s->d_counter, sizeof(int)));
+    const size_t g = (size_t)s->grid, lane = (size_t)NL * LANE_ELEMS;
+    s->line_pitch = maxW / 4 + 32;
+    if ((rc = grow(&s->d_W, &s->c_W, g * lane))) return rc;
+    if ((rc = grow(&s->d_L, &s->c_L, g * lane))) return rc;
+    if ((rc = grow(&s->d_P, &s->c_P, g * lane))) return rc;
+    if ((rc = grow(&s->d_R, &s->c_R, g * lane))) return rc;
+    if ((rc = grow(&s->d_lev, &s->c_lev, g * CTU * CTU))) return rc;
+    if ((rc = grow(&s->d_line, &s->c_line, g * (size_t)s->line_pitch))) return rc;
+    if ((rc = grow(&s->d_slots, &s->c_slots, g))) return rc;
+    std::vector<Scratch> slots(g);
+    for (size_t k = 0; k < g; k++) {
+        slots[k].W = s->d_W + k * lane; slots[k].L = s->d_L + k * lane;
+        slots[k].P = s->d_P + k * lane; slots[k].R = s->d_R + k * lane;
+        slots[k].ctu_lev = s->d_lev + k * CTU * CTU;
+        slots[k].msz_line = s->d_line + k * (size_t)s->line_pitch;
+    }
+    for (int i = 0; i < n; i++) {
+        Job& j = s->jobs[i];
+        j.img = s->d_img + s->img_off[i];
+        j.rcon = s->d_rcon + s->rcon_off[i];
+        j.out = s->d_out + s->out_off[i];
+        j.result = s->d_results + 2 * i;
+    }
+    // queue order: most CTUs first, so the tail of the persistent grid is short
+    s->order.resize(n);
+    std::iota(s->order.begin(), s->order.end(), 0);
+    std::stable_sort(s->order.begin(), s->order.end(), [&](int a, int b) {
+        return (long long)s->jobs[a].H * s->jobs[a].W > (long long)s->jobs[b].H * s->jobs[b].W;
+    });
+    CK(cudaMemcpyAsync(s->d_slots, slots.data(), g * sizeof(Scratch), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_jobs, s->jobs.data(), (size_t)n * sizeof(Job), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_order, s->order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" hevce_session* hevce_session_create(int device, int n, const int* ysz, const int* xsz, const int* qpd6) {
+    if (device_prepare(device)) return nullptr;
+    hevce_session* s = new hevce_session;
+    s->device = device;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
+        cudaEventCreate(&s->ev1) != cudaSuccess) {
+        fprintf(stderr, "libhevce_b200: cannot create stream/events on device %d\n", device);
+        hevce_session_destroy(s);
+        return nullptr;
+    }
+    if (hevce_session_configure(s, n, ysz, xsz, qpd6)) { hevce_session_destroy(s); return nullptr; }
+    return s;
+}
+
+extern "C" int hevce_session_upload(hevce_session* s, const unsigned char* const* imgs) {
+    if (!s || (s->n > 0 && !imgs)) return HEVCE_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    if (s->n == 0) return 0;
+    int rc = stage_reserve(s, s->img_total);
+    if (rc) return rc;
+    for (int i = 0; i < s->n; i++) {
+        if (!imgs[i]) return HEVCE_ERR_ARG;
+        const Job& j = s->jobs[i];
+        memcpy(s->h_stage + s->img_off[i], imgs[i], (size_t)std::min(j.src_h, j.H) * j.src_w);
+    }
+    CK(cudaMemcpyAsync(s->d_img, s->h_stage, s->img_total, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    s->h2d = (long long)s->img_total;
+    return 0;
+}
+
+extern "C" int hevce_session_encode(hevce_session* s) {
+    if (!s) return HEVCE_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    if (s->n == 0) return 0;
+    CK(cudaMemsetAsync(s->d_counter, 0, sizeof(int), s->stream));
+    CK(cudaEventRecord(s->ev0, s->stream));
+    hevce_encode_kernel<<<s->grid, NL, 0, s->stream>>>(s->d_jobs, s->d_order, s->n, s->d_slots, s->d_counter);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->ev1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaEventElapsedTime(&s->kernel_ms, s->ev0, s->ev1));
+    s->launches++;
+    return 0;
+}
+
+extern "C" int hevce_session_download(hevce_session* s, unsigned char* const* pbuffers, unsigned char* const* img_rcons, int* stream_len) {
+    if (!s || (s->n > 0 && (!pbuffers || !img_rcons))) return HEVCE_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    if (s->n == 0) return 0;
+    s->results.resize(2 * (size_t)s->n);
+    CK(cudaMemcpyAsync(s->results.data(), s->d_results, 2 * (size_t)s->n * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    size_t bytes = 0;
+    int status = 0;
+    for (int i = 0; i < s->n; i++) {
+        if (s->results[2 * i + 1] != 0 || s->results[2 * i] < 0 || s->results[2 * i] > s->jobs[i].out_cap) {
+            fprintf(stderr, "libhevce_b200: picture %d failed its consistency check (flags %d, len %d)\n", i, s->results[2 * i + 1], s->results[2 * i]);
+            status = HEVCE_ERR_STATE;
+            s->results[2 * i] = 0;
+        }
+        bytes += ((size_t)s->results[2 * i] + 15) & ~(size_t)15;
+    }
+    int rc = stage_reserve(s, s->rcon_total + bytes);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(s->h_stage, s->d_rcon, s->rcon_total, cudaMemcpyDeviceToHost, s->stream));
+    size_t off = s->rcon_total;
+    for (int i = 0; i < s->n; i++) {
+        const size_t len = (size_t)s->results[2 * i];
+        if (len) CK(cudaMemcpyAsync(s->h_stage + off, s->d_out + s->out_off[i], len, cudaMemcpyDeviceToHost, s->stream));
+        off += (len + 15) & ~(size_t)15;
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    off = s->rcon_total;
+    for (int i = 0; i < s->n; i++) {
+        if (!pbuffers[i] || !img_rcons[i]) return HEVCE_ERR_ARG;
+        const Job& j = s->jobs[i];
+        const size_t len = (size_t)s->results[2 * i];
+        memcpy(img_rcons[i], s->h_stage + s->rcon_off[i], (size_t)j.H * j.W);
+        memcpy(pbuffers[i], s->h_stage + off, len);
+        off += (len + 15) & ~(size_t)15;
+        if (stream_len) stream_len[i] = (int)len;
+    }
+    s->d2h = (long long)(s->rcon_total + bytes + 2 * (size_t)s->n * sizeof(int));
+    return status;
+}
+
+extern "C" float hevce_session_kernel_ms(const hevce_session* s) { return s ? s->kernel_ms : 0.f; }
+extern "C" int hevce_session_launches(const hevce_session* s) { return s ? s->launches : 0; }
+extern "C" int hevce_session_grid(const hevce_session* s) { return s ? s->grid : 0; }
+extern "C" long long hevce_session_h2d_bytes(const hevce_session* s) { return s ? s->h2d : 0; }
+extern "C" long long hevce_session_d2h_bytes(const hevce_session* s) { return s ? s->d2h : 0; }
+
+extern "C" void hevce_session_padded_size(const hevce_session* s, int i, int* H, int* W) {
+    *H = s->jobs[i].H;
+    *W = s->jobs[i].W;
+}
+
+extern "C" void hevce_session_destroy(hevce_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaFree(s->d_img); cudaFree(s->d_rcon); cudaFree(s->d_out); cudaFree(s->d_jobs); cudaFree(s->d_order);
+    cudaFree(s->d_results); cudaFree(s->d_counter); cudaFree(s->d_slots); cudaFree(s->d_W); cudaFree(s->d_L);
+    cudaFree(s->d_P); cudaFree(s->d_R); cudaFree(s->d_lev); cudaFree(s->d_line);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int hevce_internal_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" double hevce_measure_int_peak(int device) {
+    if (device_prepare(device)) return (double)HEVCE_ERR_CUDA;
+    int* sink = nullptr;
+    if (cudaMalloc((void**)&sink, sizeof(int)) != cudaSuccess) return (double)HEVCE_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 1 << 14, blocks = g_dev[device].sms * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        hevce_int_peak_kernel<<<blocks, threads>>>(iters, 12345 + rep, sink);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = (double)HEVCE_ERR_CUDA; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        // per iteration and thread: 8 IMAD (2 ops each) + 8 LOP3 + 8 IADD3
+        const double ops = (double)blocks * threads * iters * (8 * 2 + 8 + 8);
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}

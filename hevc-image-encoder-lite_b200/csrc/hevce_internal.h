@@ -1,0 +1,15 @@
+/* hevce_internal.h -- private C interface between hevce_api.c (plain C host code) and hevce_cuda.cu. */
+#ifndef HEVCE_INTERNAL_H
+#define HEVCE_INTERNAL_H
+#include "../../include/hevce.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+int hevce_internal_max_dim(void);
+int hevce_internal_device_count(void);
+int hevce_session_configure(hevce_session *s, int n, const int *ysz, const int *xsz, const int *qpd6);
+void hevce_session_padded_size(const hevce_session *s, int i, int *H, int *W);
+#ifdef __cplusplus
+}
+#endif
+#endif

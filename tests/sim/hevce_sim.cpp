@@ -1,0 +1,39 @@
+// hevce_sim.cpp -- TEST INFRASTRUCTURE ONLY: compiles the kernel source (csrc/hevce_core.h) for the host and runs
+// one CTA single-threaded, every PAR_FOR phase in a permuted item order.  It exists so the device logic can be
+// checked bit-for-bit against the oracle inside the build container (which has no GPU) and so that phases with
+// hidden intra-phase dependencies show up as mismatches under permutation.  The product library never links it.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "hevce_core.h"
+
+namespace hevce { int g_sim_order = 0; }
+
+extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned char* img, unsigned char* rcon,
+                                int* ysz, int* xsz, int q, int order, int max_dim, int* err) {
+    using namespace hevce;
+    g_sim_order = order;
+    static Tables tables;
+    fill_tables(tables);
+    Job job;
+    int result[2] = {0, 0};
+    job.img = img; job.rcon = rcon; job.out = out; job.result = result;
+    job.src_h = *ysz; job.src_w = *xsz;
+    job.H = (imin(*ysz, max_dim) + CTU - 1) / CTU * CTU;
+    job.W = (imin(*xsz, max_dim) + CTU - 1) / CTU * CTU;
+    job.q = q; job.out_cap = out_cap;
+    std::vector<s16> W(NL * LANE_ELEMS), L(NL * LANE_ELEMS), lev(CTU * CTU);
+    std::vector<u8> P(NL * LANE_ELEMS), R(NL * LANE_ELEMS), line(job.W / 4 + 8);
+    Scratch sc;
+    sc.W = W.data(); sc.L = L.data(); sc.P = P.data(); sc.R = R.data(); sc.ctu_lev = lev.data(); sc.msz_line = line.data();
+    Shared* sm = new Shared;
+    memset(sm, 0xA5, sizeof(Shared));   // shared memory is not zeroed on the GPU either
+    encode_picture(job, tables, *sm, sc);
+    delete sm;
+    *ysz = job.H; *xsz = job.W;
+    if (err) *err = result[1];
+    return result[0];
+}
+
+extern "C" int hevce_sim_shared_bytes() { return (int)sizeof(hevce::Shared); }
