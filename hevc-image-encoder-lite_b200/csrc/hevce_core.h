@@ -7,15 +7,19 @@
 // single-threaded *simulator* of the CTA (tests/sim/, test infrastructure only), where every PAR_FOR phase runs
 // its work items in a permuted order; bit-exactness under permutation shows the phases are race-free.
 //
-// Execution model ("bulk-synchronous lanes"):
-//   * one CTA per picture, CTUs in raster order, CUs in z-order (the CABAC state threads through the whole
-//     picture, so this order is forced -- SURVEY.md section 7.3-1);
-//   * inside a CU node every rate-distortion candidate (35 modes x {one TU, four TUs, NxN PU round}) is one
-//     *lane* (= one thread): it runs the whole pixel pipeline and a private trial arithmetic coder started from
-//     the node's snapshot, and publishes (cost, coder state, contexts);
+// Execution model ("bulk-synchronous phases", one CTA = one picture):
+//   * CTUs in raster order, CUs in z-order: the CABAC state threads through the whole picture, so this order is
+//     forced; the parallel axes are the candidates of a CU node and the batch;
+//   * pixel pipeline: the candidates of a node (35 modes x {one TU, four TUs, NxN PU}) are processed together in
+//     four phases whose work items are (candidate, line): A = predict + residual + forward column transform,
+//     B = forward row transform + RDOQ, C = coefficient-group zero-out + dequantisation + inverse column transform,
+//     D = inverse row transform + reconstruction + SSE.  All blocks live in shared memory (padded, conflict-free
+//     for both row and column items); only the final levels and reconstructions go to a per-slot L2-resident store;
+//   * entropy trials: one lane per candidate runs a private arithmetic coder (full integer state incl. the
+//     emulation-prevention bookkeeping, no byte store) from the node snapshot, reading levels one 4x4 group at a time;
 //   * thread 0 takes the arg-min with the reference's "last minimum wins" order, the CTA copies the winner's
 //     reconstruction / levels / coder state into the live state;
-//   * after each CTU the final decision tree is re-encoded once by a byte-writing coder (commit pass).
+//   * after each CTU the decided tree is re-encoded once by a byte-writing coder (commit pass).
 //
 // Behavioural parity target: /root/reference/src/HEVCe.c (cited as HEVCe.c:NNN).  Written from scratch.
 #pragma once
@@ -37,7 +41,8 @@ typedef uint32_t u32;
 // sizes
 // ------------------------------------------------------------------------------------------------------------
 constexpr int CTU = 32;
-constexpr int NL = 128;            // candidate lanes per picture slot (= threads per CTA)
+constexpr int NT = 128;            // threads per CTA
+constexpr int NCAND = 105;         // trial-coder lanes of a CU node: 35 one-TU + 35 four-TU + 35 NxN-PU candidates
 constexpr int NMODE = 35;
 constexpr int NCTX = 142;          // context bytes, same offsets as the reference struct (HEVCe.c:745-759)
 constexpr int CTXW = 36;           // context words per lane (144 bytes)
@@ -249,9 +254,9 @@ struct CtxFlat {
     u8* p;
     HEVCE_HD u8& operator[](int k) const { return p[k]; }
 };
-struct CtxLane {   // byte k of lane l lives in word (k>>2)*NL + l  -> every lane owns one bank
+struct CtxLane {   // byte k of lane l lives in word (k>>2)*NCAND + l  -> every lane owns one bank
     u8* p;         // = (u8*)lane_ctx + 4*lane
-    HEVCE_HD u8& operator[](int k) const { return p[(k >> 2) * (NL * 4) + (k & 3)]; }
+    HEVCE_HD u8& operator[](int k) const { return p[(k >> 2) * (NCAND * 4) + (k & 3)]; }
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -351,88 +356,139 @@ HEVCE_HD inline void put_remaining(Bac<E>& b, int v, int rp) {   // HEVCe.c:1154
     }
 }
 
-// residual_coding() of one TU (HEVCe.c:1173-1269).  lev(y,x) returns the quantised level.
-template <bool E, class CX, class LEV>
-HEVCE_HD inline void put_residual(Bac<E>& b, const CX& cx, int s, int m, const LEV& lev) {
+// ------------------------------------------------------------------------------------------------------------
+// residual_coding() of one TU (HEVCe.c:1173-1269), restructured around coefficient groups: the caller supplies the
+// bitmap of non-zero 4x4 groups (bit gy*8+gx), so all-zero groups cost one bin and no memory traffic, and the 16
+// levels of a coded group are staged once into a lane-private shared-memory column.
+// ------------------------------------------------------------------------------------------------------------
+struct LevSrc {            // raster block of levels; every row of a group (4 x s16) is 8-byte aligned
+    const s16* p;
+    int pitch;
+};
+struct CgBuf {             // lane-private staging column: level k of the group at word (k>>1)*NCAND + lane
+    u32* w;                // = cgbuf + lane
+    HEVCE_HD int at(int k) const { return ((const s16*)(w + (k >> 1) * NCAND))[k & 1]; }
+    HEVCE_HD void load(const LevSrc& s, int gy, int gx) const {
+        const s16* q = s.p + (gy * 4) * s.pitch + gx * 4;
+        for (int r = 0; r < 4; r++) {
+            const unsigned long long v = *(const unsigned long long*)(q + r * s.pitch);
+            w[(2 * r) * NCAND] = (u32)v;
+            w[(2 * r + 1) * NCAND] = (u32)(v >> 32);
+        }
+    }
+    HEVCE_HD void zero() const { for (int i = 0; i < 8; i++) w[i * NCAND] = 0; }
+};
+
+template <bool E, class CX>
+HEVCE_HD inline void put_residual(Bac<E>& b, const CX& cx, int s, int m, const LevSrc& src, unsigned mlo, unsigned mhi, const CgBuf& cg) {
     const Tables* tb = b.tb;
     const int st = scan_type(s, m), lg = ilog2(s), ncg = s >> 2;
-    unsigned long long cgsig = 0;
-    int last = 0;
-    for (int i = 0; i < s * s; i++) {
-        const int p = scan_pos(tb, lg, st, i), y = p >> 5, x = p & 31;
-        if (lev(y, x) != 0) { cgsig |= 1ull << ((y >> 2) * 8 + (x >> 2)); last = i; }
+    auto cgpos = [&](int g, int& cy, int& cxg) {
+        if (lg == 2) { cy = 0; cxg = 0; }
+        else if (st == 1) { cy = g >> 1; cxg = g & 1; }
+        else if (st == 2) { cy = g & 1; cxg = g >> 1; }
+        else { const int v = tb->cgdiag[lg - 3][g]; cy = v >> 3; cxg = v & 7; }
+    };
+    auto bit = [&](int cy, int cxg) -> int { const int k = cy * 8 + cxg; return (int)(((k < 32) ? (mlo >> k) : (mhi >> (k - 32))) & 1u); };
+    int gl = 0;
+    for (int g = ncg * ncg - 1; g > 0; g--) {
+        int cy, cxg;
+        cgpos(g, cy, cxg);
+        if (bit(cy, cxg)) { gl = g; break; }
     }
-    {
-        const int p = scan_pos(tb, lg, st, last);
-        put_last_xy(b, cx, s, st, p >> 5, p & 31);
-    }
-    int nz = 0, signs = 0, pat = 0, c1 = 1;
-    int absv[16];
-    for (int i = last; i >= 0; i--) {
-        const int p = scan_pos(tb, lg, st, i), y = p >> 5, x = p & 31, gy = y >> 2, gx = x >> 2;
-        const int v = lev(y, x);
-        const int cg_on = (int)((cgsig >> (gy * 8 + gx)) & 1), first_cg = !gy && !gx;
-        const int k0 = (i & 15) == 0, kend = (i & 15) == 15 || i == last;
-        if (kend) {
-            const int r = gx < ncg - 1 && ((cgsig >> (gy * 8 + gx + 1)) & 1);
-            const int d = gy < ncg - 1 && ((cgsig >> ((gy + 1) * 8 + gx)) & 1);
-            pat = (d << 1) | r;
-            nz = 0;
-            signs = 0;
-            if (!first_cg && i != last) b.put_bin(cg_on, cx[CX_SIGCG + (pat != 0)]);
+    int c1 = 1;
+    for (int g = gl; g >= 0; g--) {
+        int cy, cxg;
+        cgpos(g, cy, cxg);
+        const int on = bit(cy, cxg), first_cg = g == 0;
+        const int rgt = cxg < ncg - 1 && bit(cy, cxg + 1), dwn = cy < ncg - 1 && bit(cy + 1, cxg);
+        const int pat = (dwn << 1) | rgt;
+        if (g != gl && !first_cg) b.put_bin(on, cx[CX_SIGCG + (pat != 0)]);
+        if (!on && !first_cg) continue;
+        if (on) cg.load(src, cy, cxg); else cg.zero();
+        int kstart = 15;
+        if (g == gl) {
+            if (on) { while (kstart > 0 && cg.at(tb->scan4[st][kstart]) == 0) kstart--; }
+            else kstart = 0;
+            const int p4 = tb->scan4[st][kstart];
+            put_last_xy(b, cx, s, st, cy * 4 + (p4 >> 2), cxg * 4 + (p4 & 3));
         }
-        if (i != last && (first_cg || (cg_on && (!k0 || nz > 0))))
-            b.put_bin(v != 0, cx[CX_SIG + sig_ctx_index(tb, s, st, y, x, pat)]);
-        if (v) { absv[nz++] = iabs(v); signs = (signs << 1) | (v < 0); }
-        if (k0 && nz > 0) {
+        int nz = 0, signs = 0;
+        unsigned cls = 0;   // min(|level|,3) of the non-zero levels in coding order, 2 bits each
+        for (int k = kstart; k >= 0; k--) {
+            const int p4 = tb->scan4[st][k];
+            const int v = cg.at(p4);
+            const bool is_last = g == gl && k == kstart;
+            if (!is_last && (first_cg || k > 0 || nz > 0))
+                b.put_bin(v != 0, cx[CX_SIG + sig_ctx_index(tb, s, st, cy * 4 + (p4 >> 2), cxg * 4 + (p4 & 3), pat)]);
+            if (v) {
+                cls |= (unsigned)imin(iabs(v), 3) << (2 * nz);
+                nz++;
+                signs = (signs << 1) | (v < 0);
+            }
+        }
+        if (nz > 0) {
             const int set = (first_cg ? 0 : 2) + (c1 == 0);
             int esc = nz > 8, g2 = -1;
             c1 = 1;
             for (int j = 0; j < 8 && j < nz; j++) {
-                const int big = absv[j] > 1;
+                const int a = (int)((cls >> (2 * j)) & 3u), big = a > 1;
                 b.put_bin(big, cx[CX_ONE + 4 * set + c1]);
-                if (big) { c1 = 0; if (g2 < 0) g2 = absv[j] > 2; else esc = 1; }
+                if (big) { c1 = 0; if (g2 < 0) g2 = a > 2; else esc = 1; }
                 else if (c1 > 0 && c1 < 3) c1++;
             }
             if (c1 == 0 && g2 >= 0) { b.put_bin(g2, cx[CX_ABS + set]); esc |= g2; }
             b.put_bypass(signs, nz);
             if (esc) {
-                int base = 3, rp = 0;
-                for (int j = 0; j < nz; j++) {
-                    const int ev = absv[j] - (j < 8 ? base : 1);
-                    if (ev >= 0) { put_remaining(b, ev, rp); if (absv[j] > (3 << rp)) rp = imin(rp + 1, 4); }
-                    if (absv[j] >= 2) base = 2;
+                int base = 3, rp = 0, j = 0;
+                for (int k = kstart; k >= 0; k--) {
+                    const int a = iabs(cg.at(tb->scan4[st][k]));
+                    if (!a) continue;
+                    const int ev = a - (j < 8 ? base : 1);
+                    if (ev >= 0) { put_remaining(b, ev, rp); if (a > (3 << rp)) rp = imin(rp + 1, 4); }
+                    if (a >= 2) base = 2;
+                    j++;
                 }
             }
         }
     }
 }
 
-// One CU (HEVCe.c:1272-1340).  kind 0: 2Nx2N one TU, 1: 2Nx2N four TUs, 2: NxN.  cbf bit k set = TU k has levels.
-// lev4(k, y, x): level of TU k (k = 0 for kind 0).
-template <bool E, class CX, class LEV4>
-HEVCE_HD inline void put_cu(Bac<E>& b, const CX& cx, int s, int kind, const int* pm, const int* pl, const int* pa, int cbf, const LEV4& lev4) {
+// One CU (HEVCe.c:1272-1340).  kind 0: 2Nx2N one TU, 1: 2Nx2N four TUs, 2: NxN.
+// tu(k, src, mlo, mhi): levels + non-zero-group bitmap of TU k (k = 0 for kind 0).
+template <bool E, class CX, class TUF>
+HEVCE_HD inline void put_cu(Bac<E>& b, const CX& cx, int s, int kind, const int* pm, const int* pl, const int* pa, const CgBuf& cg, const TUF& tu) {
     if (s == 8) b.put_bin(kind != 2, cx[CX_PART]);
     put_luma_modes(b, cx, kind == 2 ? 4 : 1, pm, pl, pa);
     b.put_bin(0, cx[CX_UVPM]);
     if (kind != 2) b.put_bin(kind == 1, cx[CX_SPLIT_TU + (s == 32 ? 0 : s == 16 ? 1 : 2)]);
     b.put_bin(0, cx[CX_UVCBF]);
     b.put_bin(0, cx[CX_UVCBF]);
-    if (kind == 0) {
-        b.put_bin(cbf & 1, cx[CX_YCBF + 1]);
-        if (cbf & 1) put_residual(b, cx, s, pm[0], [&](int y, int x) { return lev4(0, y, x); });
-    } else {
-        for (int k = 0; k < 4; k++) {
-            const int on = (cbf >> k) & 1;
-            b.put_bin(on, cx[CX_YCBF]);
-            if (on) put_residual(b, cx, s >> 1, pm[kind == 2 ? k : 0], [&](int y, int x) { return lev4(k, y, x); });
-        }
+    const int ntu = kind == 0 ? 1 : 4, ts = kind == 0 ? s : s >> 1;
+    for (int k = 0; k < ntu; k++) {
+        LevSrc src;
+        unsigned mlo, mhi;
+        tu(k, src, mlo, mhi);
+        const int on = (mlo | mhi) != 0;
+        b.put_bin(on, cx[CX_YCBF + (kind == 0)]);
+        if (on) put_residual(b, cx, ts, pm[kind == 2 ? k : 0], src, mlo, mhi, cg);
     }
 }
 
 template <bool E, class CX>
 HEVCE_HD inline void put_split_cu(Bac<E>& b, const CX& cx, int s, int flag, int gtL, int gtA) {   // HEVCe.c:943-947
     if (s >= 16) b.put_bin(flag, cx[CX_SPLIT_CU + (gtL != 0) + (gtA != 0)]);
+}
+
+// bitmap of non-zero 4x4 groups of a TU (used by the commit pass; the trial path gets it from phase C)
+HEVCE_HD inline void scan_groups(const LevSrc& src, int s, unsigned& mlo, unsigned& mhi) {
+    mlo = mhi = 0;
+    for (int gy = 0; gy < (s >> 2); gy++)
+        for (int gx = 0; gx < (s >> 2); gx++) {
+            unsigned long long any = 0;
+            for (int r = 0; r < 4; r++) any |= *(const unsigned long long*)(src.p + (gy * 4 + r) * src.pitch + gx * 4);
+            if (any) { const int k = gy * 8 + gx; if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
+        }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -446,20 +502,6 @@ template <> struct Xf<8>  { static HEVCE_HD void f(const int (&x)[8], int (&y)[8
 template <> struct Xf<16> { static HEVCE_HD void f(const int (&x)[16], int (&y)[16]) { fdct16(x, y); } static HEVCE_HD void i(const int (&x)[16], int (&y)[16]) { idct16(x, y); } };
 template <> struct Xf<32> { static HEVCE_HD void f(const int (&x)[32], int (&y)[32]) { fdct32(x, y); } static HEVCE_HD void i(const int (&x)[32], int (&y)[32]) { idct32(x, y); } };
 
-// ------------------------------------------------------------------------------------------------------------
-// lane-private scratch in global memory, interleaved by lane: element i of lane l at [i*NL + l]
-// ------------------------------------------------------------------------------------------------------------
-struct LaneMem {
-    s16* W;   // working block: residual -> coefficients -> dequantised -> residual'
-    s16* L;   // quantised levels (TU-local raster; four-TU candidates: block k at k*T*T)
-    u8* P;    // prediction
-    u8* R;    // reconstruction, CU-local raster
-    HEVCE_HD s16& w(int i) const { return W[i * NL]; }
-    HEVCE_HD s16& l(int i) const { return L[i * NL]; }
-    HEVCE_HD u8& p(int i) const { return P[i * NL]; }
-    HEVCE_HD u8& r(int i) const { return R[i * NL]; }
-};
-
 HEVCE_HD inline int use_filtered(int s, int m) {   // HEVCe.c:274-280 (HEVC intraHorVerDistThres rule)
     if (s == 4 || m == 1) return 0;
     if (m == 0) return 1;
@@ -472,169 +514,6 @@ HEVCE_HD inline int intra_angle(int m) {   // HEVCe.c:282
     const int a = iabs(k);
     const int v = a == 0 ? 0 : a == 1 ? 2 : a == 2 ? 5 : a == 3 ? 9 : a == 4 ? 13 : a == 5 ? 17 : a == 6 ? 21 : a == 7 ? 26 : 32;
     return (m < 18) ? (k < 0 ? v : -v) : (k < 0 ? -v : v);
-}
-
-// One TU of one candidate: reference samples (HEVCe.c:196-257), prediction (:262-381), residual, forward
-// transform (:497-516), RDOQ (:540-595), dequantisation (:600-615), inverse transform, reconstruction, SSE.
-//   rc(y,x)  : reconstructed neighbour sample relative to the TU origin (y or x may be -1, up to 2T-1)
-//   org      : original samples of the TU, pitch CTU
-//   loff     : where this TU's levels go in lm.L ; (ry,rx,rp): where its reconstruction goes in lm.R
-// returns SSE; *nonzero = any level != 0.
-template <int T, class RC>
-HEVCE_HD inline int tu_pipeline(int q, const RdK& rk, int m, int aL, int aLB, int aA, int aAR, const RC& rc, const u8* org,
-                                const LaneMem& lm, int loff, int ry, int rx, int rp, int* nonzero) {
-    constexpr int LG = T == 4 ? 2 : T == 8 ? 3 : T == 16 ? 4 : 5;
-    // ---- reference samples
-    u8 lft[2 * T], top[2 * T];
-    int cor;
-    if (aL && aA) cor = rc(-1, -1);
-    else if (aL) cor = rc(0, -1);
-    else if (aA) cor = rc(-1, 0);
-    else cor = 128;
-    for (int i = 0; i < T; i++) lft[i] = (u8)(aL ? rc(i, -1) : cor);
-    for (int i = T; i < 2 * T; i++) lft[i] = (u8)(aLB ? rc(i, -1) : lft[T - 1]);
-    for (int i = 0; i < T; i++) top[i] = (u8)(aA ? rc(-1, i) : cor);
-    for (int i = T; i < 2 * T; i++) top[i] = (u8)(aAR ? rc(-1, i) : top[T - 1]);
-    if (use_filtered(T, m)) {
-        const int fc = (2 + lft[0] + top[0] + 2 * cor) >> 2;
-        int pl = cor, pt = cor;
-        for (int i = 0; i < 2 * T - 1; i++) {
-            const int cl = lft[i], ct = top[i];
-            lft[i] = (u8)((2 + 2 * cl + pl + lft[i + 1]) >> 2);
-            top[i] = (u8)((2 + 2 * ct + pt + top[i + 1]) >> 2);
-            pl = cl;
-            pt = ct;
-        }
-        cor = fc;
-    }
-    // ---- prediction -> lm.P, residual -> lm.W
-    const bool edge = T <= 16;
-    if (m == 0) {
-        for (int y = 0; y < T; y++)
-            for (int x = 0; x < T; x++)
-                lm.p(y * T + x) = (u8)((T + (T - 1 - x) * lft[y] + (x + 1) * top[T] + (T - 1 - y) * top[x] + (y + 1) * lft[T]) >> (LG + 1));
-    } else if (m == 1) {
-        int dc = T;
-        for (int i = 0; i < T; i++) dc += lft[i] + top[i];
-        dc >>= LG + 1;
-        for (int i = 0; i < T * T; i++) lm.p(i) = (u8)dc;
-        if (edge) {
-            lm.p(0) = (u8)((2 + 2 * dc + lft[0] + top[0]) >> 2);
-            for (int i = 1; i < T; i++) {
-                lm.p(i) = (u8)((2 + 3 * dc + top[i]) >> 2);
-                lm.p(i * T) = (u8)((2 + 3 * dc + lft[i]) >> 2);
-            }
-        }
-    } else if (m == 10) {
-        for (int y = 0; y < T; y++)
-            for (int x = 0; x < T; x++) lm.p(y * T + x) = lft[y];
-        if (edge)
-            for (int x = 0; x < T; x++) lm.p(x) = (u8)iclip(((top[x] - cor) >> 1) + lft[0], 0, 255);
-    } else if (m == 26) {
-        for (int y = 0; y < T; y++)
-            for (int x = 0; x < T; x++) lm.p(y * T + x) = top[x];
-        if (edge)
-            for (int y = 0; y < T; y++) lm.p(y * T) = (u8)iclip(((lft[y] - cor) >> 1) + top[0], 0, 255);
-    } else {
-        const bool horiz = m < 18;
-        const int ang = intra_angle(m), aa = iabs(ang), inv = (8192 + aa / 2) / aa;   // HEVCe.c:283
-        const u8* mainb = horiz ? lft : top;
-        const u8* side = horiz ? top : lft;
-        u8 rf[3 * T + 4];
-        u8* r = rf + T;
-        r[0] = (u8)cor;
-        for (int i = 0; i < 2 * T; i++) r[1 + i] = mainb[i];
-        r[2 * T + 1] = 0;   // read with weight 0 by modes 2 / 34 (HEVCe.c:371-373)
-        const int lastneg = (T * ang) >> 5;
-        for (int i = -1; i > lastneg; i--) r[i] = side[((128 - inv * i) >> 8) - 1];
-        for (int i = 0; i < T; i++) {
-            const int off = ang * (i + 1), oi = off >> 5, of = off & 31;
-            for (int j = 0; j < T; j++) {
-                const u8 pv = (u8)(((32 - of) * r[oi + j + 1] + of * r[oi + j + 2] + 16) >> 5);
-                if (horiz) lm.p(j * T + i) = pv; else lm.p(i * T + j) = pv;
-            }
-        }
-    }
-    for (int y = 0; y < T; y++)
-        for (int x = 0; x < T; x++) lm.w(y * T + x) = (s16)((int)org[y * CTU + x] - lm.p(y * T + x));
-    // ---- forward transform: columns (>> a), rows (>> a+7)
-    {
-        constexpr int A1 = LG - 1, A2 = LG + 6;
-        int v[T], o[T];
-        for (int x = 0; x < T; x++) {
-            for (int y = 0; y < T; y++) v[y] = lm.w(y * T + x);
-            Xf<T>::f(v, o);
-            for (int k = 0; k < T; k++) lm.w(k * T + x) = (s16)((o[k] + (1 << A1 >> 1)) >> A1);
-        }
-        for (int y = 0; y < T; y++) {
-            for (int x = 0; x < T; x++) v[x] = lm.w(y * T + x);
-            Xf<T>::f(v, o);
-            for (int k = 0; k < T; k++) lm.w(y * T + k) = (s16)((o[k] + (1 << A2 >> 1)) >> A2);
-        }
-    }
-    // ---- RDOQ + dequantisation, one 4x4 coefficient group at a time
-    int any = 0;
-    {
-        const int dsh = 10 - LG, sh = 21 - LG + q, add = 1 << sh >> 1, thr = 9 << sh >> 2, qs = 7 - LG + q;
-        for (int cy = 0; cy < T; cy += 4)
-            for (int cx = 0; cx < T; cx += 4) {
-                int lv[16], sum = 0, nzg = 0;
-                for (int k = 0; k < 16; k++) {
-                    const int c = lm.w((cy + (k >> 2)) * T + cx + (k & 3));
-                    const int dl = iabs(c) << 14;                    // |c| <= 32640, no clamp can trigger (HEVCe.c:566)
-                    int lvl = iclip((dl + add) >> sh, -32768, 32767);
-                    const int lo = imax(0, lvl - 2);
-                    int best = IMAX, pick = 0;
-                    for (; lvl >= lo; lvl--) {
-                        const int d1 = iabs(dl - (lvl << sh)) >> dsh;
-                        const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
-                        int rate;                                    // HEVCe.c:526-535
-                        if (lvl < 6) rate = lvl == 0 ? 0 : lvl == 1 ? 70000 : lvl == 2 ? 90000 : lvl == 3 ? 92000 : lvl == 4 ? 157536 : 190304;
-                        else rate = 92000 + ((4 + 2 * (bitlen((unsigned)(lvl - 5)) - 1)) << 15);
-                        const int cost = rd_cost(rk, d, rate);
-                        if (cost < best) { best = cost; pick = lvl; }
-                    }
-                    lv[k] = c < 0 ? -pick : pick;
-                    nzg |= pick;
-                    sum += imin(dl, thr);
-                }
-                if (sum < thr) nzg = 0;
-                any |= nzg;
-                for (int k = 0; k < 16; k++) {
-                    const int idx = (cy + (k >> 2)) * T + cx + (k & 3);
-                    const int l = nzg ? lv[k] : 0;
-                    lm.l(loff + idx) = (s16)l;
-                    lm.w(idx) = (s16)iclip(l * (1 << qs), -32768, 32767);
-                }
-            }
-    }
-    *nonzero = any != 0;
-    // ---- inverse transform + reconstruction + SSE
-    int sse = 0;
-    {
-        int v[T], o[T];
-        if (any) {
-            for (int x = 0; x < T; x++) {
-                for (int y = 0; y < T; y++) v[y] = lm.w(y * T + x);
-                Xf<T>::i(v, o);
-                for (int k = 0; k < T; k++) lm.w(k * T + x) = (s16)iclip((o[k] + 64) >> 7, -32768, 32767);
-            }
-        }
-        for (int y = 0; y < T; y++) {
-            if (any) {
-                for (int x = 0; x < T; x++) v[x] = lm.w(y * T + x);
-                Xf<T>::i(v, o);
-            }
-            for (int x = 0; x < T; x++) {
-                const int res = any ? iclip((o[x] + 2048) >> 12, -32768, 32767) : 0;
-                const int rec = iclip(res + lm.p(y * T + x), 0, 255);
-                const int d = (int)org[y * CTU + x] - rec;
-                lm.r((ry + y) * rp + rx + x) = (u8)rec;
-                sse += d * d;
-            }
-        }
-    }
-    return sse;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -653,41 +532,57 @@ struct Job {
 
 enum { ERR_OVERFLOW = 1, ERR_COMMIT_MISMATCH = 2 };
 
-struct Scratch {       // per picture slot, global memory
-    s16* W; s16* L; u8* P; u8* R;   // NL * LANE_ELEMS each
-    s16* ctu_lev;                   // CTU*CTU final levels of the current CTU
-    u8* msz_line;                   // CU-size map row of the CTU row above, W/4 entries
+constexpr int LEV_STRIDE = CTU * CTU;   // per-candidate level store (all TUs of the candidate)
+constexpr int NREC = 70;                // candidates whose reconstruction is kept (one-TU + four-TU)
+
+struct Scratch {       // per picture slot, global memory (L2-resident working set)
+    s16* glev;         // [NCAND][LEV_STRIDE] final levels of every candidate of the current node
+    u8* grec;          // [NREC][CTU*CTU] reconstruction of every non-NxN candidate, CU-local raster
+    s16* ctu_lev;      // CTU*CTU final levels of the current CTU (pitch CTU)
+    u8* msz_line;      // CU-size map row of the CTU row above, W/4 entries
 };
+
+constexpr int POOL_BYTES = 29440;
+constexpr int AUX_CODER = 23552;                 // pool tail: trial-coder results + group staging (free whenever they are used)
+constexpr int AUX_CGBUF = AUX_CODER + 1968;
 
 struct Shared {
     Tables tb;
-    u8 ctx0[144];                   // freshly initialised contexts for this picture's qpd6
+    alignas(16) u8 pool[POOL_BYTES];    // per-node carve-up: work blocks, predictions, borders (see Plan<S>)
+    u32 lane_ctx[CTXW * NCAND];         // lane-private context sets, word-interleaved
+    alignas(8) u8 ctx0[144];            // freshly initialised contexts for this picture's qpd6
+    alignas(8) u8 live_ctx[144];
+    alignas(8) u8 snap_ctx[3][144];
+    alignas(8) u8 start_ctx[144];
+    alignas(8) u8 nxn_ctx[144];
+    alignas(8) s16 nxn_lev[4][16];
     u8 orig[CTU * CTU];
     u8 win[(CTU + 1) * WP];
-    u8 msz[81], mpm[81];            // [1+uy][1+ux], 4x4 units; row 0 / col 0 = neighbours
-    u8 kind[16];                    // per 8x8 unit: 0 one TU, 1 four TUs, 2 NxN
-    Coder live;  u8 live_ctx[144];
-    Coder snap[3]; u8 snap_ctx[3][144];
-    Coder start; u8 start_ctx[144];
-    Coder nxn_coder; u8 nxn_ctx[144];
-    int cand_cost[NL];
-    Coder cand_coder[NL];
-    int cand_cbf[NL];
-    u32 lane_ctx[CTXW * NL];
-    s16 nxn_lev[4][16];
-    int nxn_pm[4], nxn_cbf, nxn_cost;
+    u8 msz[81], mpm[81];                // [1+uy][1+ux], 4x4 units; row 0 / col 0 = neighbours
+    u8 kind[16];                        // per 8x8 unit: 0 one TU, 1 four TUs, 2 NxN
+    Coder live, snap[3], start, nxn_coder;
+    int cand_sse[NCAND], cand_bits[NCAND];
+    unsigned cgnz[NCAND][4];            // non-zero-group bitmaps: one-TU: [0],[1] = low/high word; else [tu]
+    int nxn_pm[4], nxn_cost;
+    unsigned nxn_nz[4];
     int part_sse[CTU];
-    int win_item;                   // decision of the current node: -1 keep split, 0..NL-1 lane, NL = NxN
-    int pu_best;
+    int win_item;                       // decision of the current node: -1 keep split, 0..NREC-1 candidate, NCAND = NxN
     int stream_pos;
     int error;
 };
 
+HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CODER); }
+HEVCE_HD inline u32* cg_staging(Shared& sm) { return (u32*)(sm.pool + AUX_CGBUF); }
+static_assert(AUX_CGBUF + 8 * NCAND * 4 <= POOL_BYTES, "pool tail too small");
+
 // work-item phases.  On the GPU a phase is a strided loop over the CTA's threads followed by __syncthreads();
 // in the simulator it is a loop over the items in a permuted order.
 #if defined(__CUDA_ARCH__)
-#define PAR_FOR(item, n) for (int item = (int)threadIdx.x; item < (n); item += (int)blockDim.x)
+#define PAR_FOR(item, n) for (int item = (int)threadIdx.x; item < (n); item += NT)
+#define PAR_FOR_OFF(item, n, off) for (int item = (int)((threadIdx.x + NT - ((off) & (NT - 1))) & (NT - 1)); item < (n); item += NT)
 #define PHASE_END() __syncthreads()
+#define HEVCE_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define HEVCE_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #else
 extern int g_sim_order;   // 0 forward, 1 reverse, >=2 multiplicative permutation
 inline int sim_item(int i, int n) {
@@ -699,16 +594,11 @@ inline int sim_item(int i, int n) {
     return (int)(((long long)i * a + 7) % n);
 }
 #define PAR_FOR(item, n) for (int item##_i = 0, item = 0; item##_i < (n) && ((item = sim_item(item##_i, (n))), true); item##_i++)
+#define PAR_FOR_OFF(item, n, off) PAR_FOR(item, n)
 #define PHASE_END() ((void)0)
+#define HEVCE_ATOMIC_OR(p, v) (*(p) |= (v))
+#define HEVCE_ATOMIC_ADD(p, v) (*(p) += (v))
 #endif
-
-// candidate lanes: thread index -> (step, mode).  Steps: 0 = 2Nx2N one TU, 1 = 2Nx2N four TUs, 2 = NxN PU round.
-// Modes 0..31 of each step share a warp; the three leftover modes of every step are packed behind them.
-HEVCE_HD inline int lane_item(int nsteps, int step, int mode) { return mode < 32 ? step * 32 + mode : nsteps * 32 + step * 3 + (mode - 32); }
-HEVCE_HD inline void lane_decode(int nsteps, int item, int& step, int& mode) {
-    if (item < nsteps * 32) { step = item >> 5; mode = item & 31; }
-    else { const int r = item - nsteps * 32; step = r / 3; mode = 32 + r % 3; }
-}
 
 struct Avail { int L, LB, A, AR; };
 HEVCE_HD inline Avail sub_avail(const Avail& a, int k) {   // HEVCe.c:1376-1379
@@ -720,85 +610,378 @@ HEVCE_HD inline Avail sub_avail(const Avail& a, int k) {   // HEVCe.c:1376-1379
     return r;
 }
 
-HEVCE_HD inline LaneMem lane_mem(const Scratch& sc, int lane) {
-    LaneMem lm;
-    lm.W = sc.W + lane; lm.L = sc.L + lane; lm.P = sc.P + lane; lm.R = sc.R + lane;
-    return lm;
-}
-
 // window sample relative to CTU pixel (y,x); y or x may be -1
 #define HEVCE_WIN(sm, y, x) ((sm).win[(1 + (y)) * WP + 1 + (x)])
 
-// One trial lane of a CU node of size S at CTU position (y0,x0).
-template <int S>
-HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int q, int item, int step, int mode, int y0, int x0, const Avail& av,
-                                int depth, int gtL, int gtA, int pmL, int pmA) {
-    constexpr int H = S / 2;
-    const LaneMem lm = lane_mem(sc, item);
-    const RdK rk = rd_consts(q);
-    const u8* org = sm.orig + y0 * CTU + x0;
-    int sse = 0, cbf = 0;
-    if (step == 0) {
-        int nzf;
-        auto rc = [&](int y, int x) -> int { return HEVCE_WIN(sm, y0 + y, x0 + x); };
-        sse = tu_pipeline<S>(q, rk, mode, av.L, av.LB, av.A, av.AR, rc, org, lm, 0, 0, 0, S, &nzf);
-        cbf = nzf;
-    } else {
-        for (int k = 0; k < 4; k++) {
-            const int oy = (k >> 1) * H, ox = (k & 1) * H;
-            const Avail sa = sub_avail(av, k);
-            int nzf;
-            auto rc = [&](int y, int x) -> int {   // inside the CU: this candidate's own reconstruction
-                const int yy = oy + y, xx = ox + x;
-                if (yy >= 0 && xx >= 0 && yy < S && xx < S) return lm.r(yy * S + xx);
-                return HEVCE_WIN(sm, y0 + yy, x0 + xx);
-            };
-            sse += tu_pipeline<H>(q, rk, mode, sa.L, sa.LB, sa.A, sa.AR, rc, org + oy * CTU + ox, lm, k * H * H, oy, ox, S, &nzf);
-            cbf |= nzf << k;
-        }
-    }
-    // trial entropy coding from the node snapshot
-    Bac<false> b;
-    b.c = sm.snap[depth];
-    b.out = nullptr; b.cap = 0; b.tb = &sm.tb;
-    const CtxLane cx = {(u8*)sm.lane_ctx + 4 * item};
-    for (int k = 0; k < NCTX; k++) cx[k] = sm.snap_ctx[depth][k];
-    put_split_cu(b, cx, S, 0, gtL, gtA);
-    const int ts = step == 0 ? S : H;
-    put_cu(b, cx, S, step, &mode, &pmL, &pmA, cbf, [&](int k, int y, int x) -> int { return lm.l(k * H * H + y * ts + x); });
-    sm.cand_cost[item] = rd_cost(rk, sse, coder_len(b.c) - coder_len(sm.snap[depth]));
-    sm.cand_coder[item] = b.c;
-    sm.cand_cbf[item] = cbf;
+// trial lanes: thread -> candidate.  Modes 0..31 of a step share a warp, the 3 leftover modes are packed behind.
+HEVCE_HD inline int lane_to_cand(int nsteps, int t) {   // returns step*35+mode, or -1
+    if (t < nsteps * 32) return (t >> 5) * NMODE + (t & 31);
+    const int r = t - nsteps * 32;
+    if (r >= nsteps * 3) return -1;
+    return (r / 3) * NMODE + 32 + r % 3;
 }
 
-// One lane of an NxN PU round (HEVCe.c:1499-1528): 4x4 pipeline + residual coding from a fresh coder.
-HEVCE_HD inline void pu_lane(Shared& sm, const Scratch& sc, int q, int item, int mode, int y0, int x0, const Avail& av, int k) {
-    const LaneMem lm = lane_mem(sc, item);
-    const RdK rk = rd_consts(q);
-    const int oy = (k >> 1) * 4, ox = (k & 1) * 4;
-    const Avail sa = sub_avail(av, k);
-    int nzf;
-    auto rc = [&](int y, int x) -> int { return HEVCE_WIN(sm, y0 + oy + y, x0 + ox + x); };
-    const int sse = tu_pipeline<4>(q, rk, mode, sa.L, sa.LB, sa.A, sa.AR, rc, sm.orig + (y0 + oy) * CTU + x0 + ox, lm, 0, 0, 0, 4, &nzf);
+// ------------------------------------------------------------------------------------------------------------
+// pixel pipeline: one group = the same TU (position, size T) of n candidates with consecutive modes
+// ------------------------------------------------------------------------------------------------------------
+struct Grp {
+    int n;              // candidates in this group (0 = group unused this round)
+    int cand0;          // index of local candidate 0 in the per-node arrays (glev, cand_sse, cgnz, ...)
+    int mode0;          // its intra mode; local candidate c has mode0 + c
+    int ty, tx;         // TU origin in CTU coordinates
+    Avail av;           // neighbour availability of this TU
+    int priv;           // 1: samples inside the CU come from the candidate's own reconstruction (four-TU candidates)
+    int cuy, cux, cus;  // CU origin / size
+    int tu;             // TU index inside the candidate (levels at tu*T*T, bitmap word)
+    int one_tu;         // 1: one-TU candidate (bitmap uses words 0/1)
+    int grec;           // 1: reconstruction rows also go to the global store (cand0 < NREC)
+    s16* blk;           // [n][T*T+T]   residual -> coefficients -> tentative levels -> inverse intermediate
+    u8* pred;           // [n][T*T]
+    int* psum;          // [n][T*T/4]   per (row, group column) sums for the group zero-out
+    u8* bord;           // shared: [2][4T+4] (unfiltered, filtered); private: [n][4T+4]
+    u8* rec;            // [n][rec_stride] candidate-private reconstruction, pitch rec_pitch, or nullptr
+    int rec_stride, rec_pitch;
+};
+
+template <int T> struct Dim {
+    static constexpr int LG = T == 4 ? 2 : T == 8 ? 3 : T == 16 ? 4 : 5;
+    static constexpr int BLK = T * T + T;      // padded so that column items of neighbouring candidates hit distinct banks
+    static constexpr int BS = 4 * T + 4;       // border array: [pad][2T left, bottom first][corner][2T top][pad]
+};
+
+// phase 0: reference samples (HEVCe.c:196-257) into the unified border array b[0..4T]: b[2T] = corner,
+// b[2T-1-i] = left[i], b[2T+1+i] = top[i]; the [1 2 1] filter is then uniform over the array.
+template <int T>
+HEVCE_HD inline void border_item(Shared& sm, const Grp& g, int item) {
+    constexpr int NB = 4 * T + 1, BS = Dim<T>::BS;
+    const int which = item / NB, j = item - which * NB;   // private: candidate index; shared: 0 unfiltered / 1 filtered
+    const int cand = g.priv ? which : 0;
+    auto nb = [&](int y, int x) -> int {
+        const int yy = g.ty + y, xx = g.tx + x;
+        if (g.priv) {
+            const int cy = yy - g.cuy, cx = xx - g.cux;
+            if (cy >= 0 && cx >= 0 && cy < g.cus && cx < g.cus) return g.rec[cand * g.rec_stride + cy * g.rec_pitch + cx];
+        }
+        return HEVCE_WIN(sm, yy, xx);
+    };
+    const Avail& a = g.av;
+    int cor;
+    if (a.L && a.A) cor = nb(-1, -1);
+    else if (a.L) cor = nb(0, -1);
+    else if (a.A) cor = nb(-1, 0);
+    else cor = 128;
+    auto u = [&](int jj) -> int {
+        if (jj == 2 * T) return cor;
+        if (jj < 2 * T) {
+            const int i = 2 * T - 1 - jj;
+            if (i < T) return a.L ? nb(i, -1) : cor;
+            return a.LB ? nb(i, -1) : (a.L ? nb(T - 1, -1) : cor);
+        }
+        const int i = jj - 2 * T - 1;
+        if (i < T) return a.A ? nb(-1, i) : cor;
+        return a.AR ? nb(-1, i) : (a.A ? nb(-1, T - 1) : cor);
+    };
+    int v = u(j);
+    const bool filt = g.priv ? use_filtered(T, g.mode0 + cand) != 0 : which == 1;
+    if (T > 4 && filt && j > 0 && j < 4 * T) v = (2 + 2 * v + u(j - 1) + u(j + 1)) >> 2;
+    g.bord[which * BS + 1 + j] = (u8)v;
+}
+
+// phase A: prediction of column x (HEVCe.c:262-381), residual, forward column transform (HEVCe.c:514)
+template <int T>
+HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
+    constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, BS = Dim<T>::BS;
+    const int c = item >> LG, x = item & (T - 1), m = g.mode0 + c;
+    const int bsel = g.priv ? c : (T > 4 && use_filtered(T, m));
+    const u8* B = g.bord + bsel * BS + 1 + 2 * T;   // B[k]: k > 0 top[k-1], k < 0 left[-k-1], 0 corner
+    const u8* org = sm.orig + g.ty * CTU + g.tx + x;
+    u8* pp = g.pred + c * (T * T) + x;
+    if (x == 0) {   // per-candidate accumulators of this TU
+        const int ci = g.cand0 + c;
+        if (g.one_tu) { sm.cgnz[ci][0] = 0; sm.cgnz[ci][1] = 0; sm.cand_sse[ci] = 0; }
+        else { sm.cgnz[ci][g.tu] = 0; if (g.tu == 0 || !g.priv) sm.cand_sse[ci] = 0; }
+    }
+    int v[T], o[T];
+    const bool edge = T <= 16;
+    if (m == 0) {
+        const int tr = B[T + 1], bl = B[-T - 1], tx = B[1 + x];
+#pragma unroll
+        for (int y = 0; y < T; y++) v[y] = ((T - 1 - x) * B[-1 - y] + (x + 1) * tr + (T - 1 - y) * tx + (y + 1) * bl + T) >> (LG + 1);
+    } else if (m == 1) {
+        int dc = T;
+        for (int i = 0; i < T; i++) dc += B[-1 - i] + B[1 + i];
+        dc >>= LG + 1;
+#pragma unroll
+        for (int y = 0; y < T; y++) v[y] = dc;
+        if (edge) {
+            if (x == 0) {
+#pragma unroll
+                for (int y = 1; y < T; y++) v[y] = (2 + 3 * dc + B[-1 - y]) >> 2;
+                v[0] = (2 + 2 * dc + B[-1] + B[1]) >> 2;
+            } else v[0] = (2 + 3 * dc + B[1 + x]) >> 2;
+        }
+    } else if (m == 10) {
+#pragma unroll
+        for (int y = 0; y < T; y++) v[y] = B[-1 - y];
+        if (edge) v[0] = iclip(((B[1 + x] - B[0]) >> 1) + B[-1], 0, 255);
+    } else if (m == 26) {
+        const int t = B[1 + x];
+#pragma unroll
+        for (int y = 0; y < T; y++) v[y] = t;
+        if (edge && x == 0) {
+#pragma unroll
+            for (int y = 0; y < T; y++) v[y] = iclip(((B[-1 - y] - B[0]) >> 1) + t, 0, 255);
+        }
+    } else {
+        const int ang = intra_angle(m), aa = iabs(ang), inv = (8192 + aa / 2) / aa;   // HEVCe.c:283
+        if (m < 18) {   // horizontal family: main arm = left, projected side = top
+            const int off = ang * (x + 1), oi = off >> 5, of = off & 31;
+            auto R = [&](int k) -> int { return k >= 0 ? B[-k] : B[(128 - inv * k) >> 8]; };
+            int prev = R(oi + 1);
+#pragma unroll
+            for (int y = 0; y < T; y++) {
+                const int nxt = R(oi + y + 2);
+                v[y] = ((32 - of) * prev + of * nxt + 16) >> 5;
+                prev = nxt;
+            }
+        } else {        // vertical family: main arm = top, projected side = left
+            auto R = [&](int k) -> int { return k >= 0 ? B[k] : B[-((128 - inv * k) >> 8)]; };
+#pragma unroll
+            for (int y = 0; y < T; y++) {
+                const int off = ang * (y + 1), oi = off >> 5, of = off & 31, k = oi + x + 1;
+                v[y] = ((32 - of) * R(k) + of * R(k + 1) + 16) >> 5;
+            }
+        }
+    }
+#pragma unroll
+    for (int y = 0; y < T; y++) {
+        pp[y * T] = (u8)v[y];
+        v[y] = (int)org[y * CTU] - v[y];
+    }
+    Xf<T>::f(v, o);
+    s16* bp = g.blk + c * BLK + x;
+    constexpr int A1 = LG - 1;
+#pragma unroll
+    for (int k = 0; k < T; k++) bp[k * T] = (s16)((o[k] + (1 << A1 >> 1)) >> A1);
+}
+
+// phase B: forward row transform (HEVCe.c:515) + per-coefficient RDOQ (HEVCe.c:563-586); tentative levels replace
+// the coefficients in place, the clamped magnitudes are summed per (row, group column) for the zero-out test
+template <int T>
+HEVCE_HD inline void phase_b_item(Shared& sm, const Grp& g, int item, int q, const RdK& rk) {
+    constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, A2 = LG + 6;
+    const int c = item >> LG, y = item & (T - 1);
+    s16* bp = g.blk + c * BLK + y * T;
+    int v[T], o[T];
+#pragma unroll
+    for (int x = 0; x < T; x++) v[x] = bp[x];
+    Xf<T>::f(v, o);
+    const int dsh = 10 - LG, sh = 21 - LG + q, add = 1 << sh >> 1, thr = 9 << sh >> 2;
+    int* ps = g.psum + c * (T * T / 4) + y * (T / 4);
+#pragma unroll
+    for (int gx = 0; gx < T / 4; gx++) {
+        int sum = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int x = gx * 4 + e;
+            const int cf = (o[x] + (1 << A2 >> 1)) >> A2;
+            const int dl = iabs(cf) << 14;                       // |cf| <= 32640: the clamps of HEVCe.c:566 cannot trigger
+            int lvl = (dl + add) >> sh;
+            int pick = 0;
+            if (lvl > 0) {
+                const int lo = imax(0, lvl - 2);
+                int best = IMAX;
+                for (; lvl >= lo; lvl--) {
+                    const int d1 = iabs(dl - (lvl << sh)) >> dsh;
+                    const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
+                    int rate;                                    // HEVCe.c:526-535
+                    if (lvl < 6) rate = lvl == 0 ? 0 : lvl == 1 ? 70000 : lvl == 2 ? 90000 : lvl == 3 ? 92000 : lvl == 4 ? 157536 : 190304;
+                    else rate = 92000 + ((4 + 2 * (bitlen((unsigned)(lvl - 5)) - 1)) << 15);
+                    const int cost = rd_cost(rk, d, rate);
+                    if (cost < best) { best = cost; pick = lvl; }
+                }
+            }
+            bp[x] = (s16)(cf < 0 ? -pick : pick);
+            sum += imin(dl, thr);
+        }
+        ps[gx] = sum;
+    }
+}
+
+// phase C: group zero-out (HEVCe.c:589-592), final levels -> global store + non-zero-group bitmap, dequantisation
+// (HEVCe.c:600-615), inverse column transform (HEVCe.c:514 with inverse=1)
+template <int T>
+HEVCE_HD inline void phase_c_item(Shared& sm, const Scratch& sc, const Grp& g, int item, int q) {
+    constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK;
+    const int c = item >> LG, x = item & (T - 1), gx = x >> 2, ci = g.cand0 + c;
+    s16* bp = g.blk + c * BLK + x;
+    const int* ps = g.psum + c * (T * T / 4) + gx;
+    s16* lp = sc.glev + (size_t)ci * LEV_STRIDE + g.tu * (T * T) + x;
+    const int sh = 21 - LG + q, thr = 9 << sh >> 2, qs = 7 - LG + q;
+    int v[T], o[T];
+    unsigned mlo = 0, mhi = 0;
+    int anyc = 0;
+#pragma unroll
+    for (int gy = 0; gy < T / 4; gy++) {
+        const int sum = ps[(gy * 4) * (T / 4)] + ps[(gy * 4 + 1) * (T / 4)] + ps[(gy * 4 + 2) * (T / 4)] + ps[(gy * 4 + 3) * (T / 4)];
+        const bool keep = sum >= thr;
+        int nzc = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int y = gy * 4 + r;
+            const int l = keep ? (int)bp[y * T] : 0;
+            lp[y * T] = (s16)l;
+            nzc |= l;
+            v[y] = iclip(l * (1 << qs), -32768, 32767);
+        }
+        if (nzc) {
+            const int k = gy * 8 + gx;
+            if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32);
+            anyc = 1;
+        }
+    }
+    if (g.one_tu) {
+        if (mlo) HEVCE_ATOMIC_OR(&sm.cgnz[ci][0], mlo);
+        if (mhi) HEVCE_ATOMIC_OR(&sm.cgnz[ci][1], mhi);
+    } else if (mlo) HEVCE_ATOMIC_OR(&sm.cgnz[ci][g.tu], mlo);
+    if (anyc) {
+        Xf<T>::i(v, o);
+#pragma unroll
+        for (int k = 0; k < T; k++) bp[k * T] = (s16)iclip((o[k] + 64) >> 7, -32768, 32767);
+    } else {
+#pragma unroll
+        for (int k = 0; k < T; k++) bp[k * T] = 0;
+    }
+}
+
+// phase D: inverse row transform (HEVCe.c:515 with inverse=1), reconstruction, SSE (HEVCe.c:165-174)
+template <int T>
+HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, int item) {
+    constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK;
+    const int c = item >> LG, y = item & (T - 1), ci = g.cand0 + c;
+    const unsigned nzw = g.one_tu ? (sm.cgnz[ci][0] | sm.cgnz[ci][1]) : sm.cgnz[ci][g.tu];
+    const s16* bp = g.blk + c * BLK + y * T;
+    const u8* pp = g.pred + c * (T * T) + y * T;
+    const u8* org = sm.orig + (g.ty + y) * CTU + g.tx;
+    int v[T], o[T];
+    if (nzw) {
+#pragma unroll
+        for (int x = 0; x < T; x++) v[x] = bp[x];
+        Xf<T>::i(v, o);
+    }
+    const int ry = g.ty - g.cuy + y, rx = g.tx - g.cux;
+    u8* rs = g.rec ? g.rec + c * g.rec_stride + ry * g.rec_pitch + rx : nullptr;
+    u8* rg = g.grec ? sc.grec + (size_t)ci * (CTU * CTU) + ry * g.cus + rx : nullptr;
+    int sse = 0;
+#pragma unroll
+    for (int x = 0; x < T; x++) {
+        const int res = nzw ? iclip((o[x] + 2048) >> 12, -32768, 32767) : 0;
+        const int rec = iclip(res + pp[x], 0, 255);
+        const int d = (int)org[x] - rec;
+        sse += d * d;
+        if (rs) rs[x] = (u8)rec;
+        if (rg) rg[x] = (u8)rec;
+    }
+    HEVCE_ATOMIC_ADD(&sm.cand_sse[ci], sse);
+}
+
+template <int T>
+HEVCE_HD inline void run_borders(Shared& sm, const Grp& g, int off) {
+    if (g.n == 0) return;
+    const int n = (g.priv ? g.n : (T > 4 ? 2 : 1)) * (4 * T + 1);
+    PAR_FOR_OFF(item, n, off) border_item<T>(sm, g, item);
+}
+
+// shared-memory carve-up of the pool for a node of size S: group 0 = one-TU candidates (T = S), group 1 = four-TU
+// candidates (T = S/2), group 2 (S = 8 only) = NxN PU candidates (T = 4)
+template <int S> struct Plan {
+    static constexpr int H = S / 2;
+    static constexpr int N0 = S == 8 ? 35 : S == 16 ? 9 : 2;     // one-TU candidates per round
+    static constexpr int N1 = S == 32 ? 7 : 35;                  // four-TU candidates per chunk
+    static constexpr int ROUNDS = S == 32 ? 20 : 4;              // 32: 5 chunks of 7 modes x 4 sub-TUs
+    static constexpr int al(int v) { return (v + 15) & ~15; }
+    // group 0
+    static constexpr int BLK0 = 0;
+    static constexpr int PRED0 = BLK0 + al(N0 * Dim<S>::BLK * 2);
+    static constexpr int PSUM0 = PRED0 + al(N0 * S * S);
+    static constexpr int BORD0 = PSUM0 + al(N0 * S * S);         // S*S/4 ints
+    static constexpr int END0 = BORD0 + al(2 * Dim<S>::BS);
+    // group 1
+    static constexpr int BLK1 = END0;
+    static constexpr int PRED1 = BLK1 + al(N1 * Dim<H>::BLK * 2);
+    static constexpr int PSUM1 = PRED1 + al(N1 * H * H);
+    static constexpr int BORD1 = PSUM1 + al(N1 * H * H);
+    static constexpr int REC1 = BORD1 + al(N1 * Dim<H>::BS);
+    static constexpr int END1 = REC1 + al(N1 * S * S);
+    // group 2 (S == 8)
+    static constexpr int BLK2 = END1;
+    static constexpr int PRED2 = BLK2 + al(35 * Dim<4>::BLK * 2);
+    static constexpr int PSUM2 = PRED2 + al(35 * 16);
+    static constexpr int BORD2 = PSUM2 + al(35 * 16);
+    static constexpr int REC2 = BORD2 + al(2 * Dim<4>::BS);
+    static constexpr int END2 = REC2 + al(35 * 16);
+    static constexpr int TOTAL = S == 8 ? END2 : END1;
+    static_assert(TOTAL <= POOL_BYTES, "shared-memory pool too small");
+    static_assert(S != 8 || TOTAL <= AUX_CODER, "8x8 pipeline buffers overlap the trial-coder results");
+};
+
+template <bool E>
+HEVCE_HD inline Bac<E> make_bac(const Coder& c, const Tables* tb) {
+    Bac<E> b;
+    b.c = c; b.out = nullptr; b.cap = 0; b.tb = tb;
+    return b;
+}
+
+// trial entropy coding of one non-NxN candidate from the node snapshot (HEVCe.c:1434-1438, 1470-1474)
+template <int S>
+HEVCE_HD inline void trial_cabac(Shared& sm, const Scratch& sc, int cand, int depth, int gtL, int gtA, int pmL, int pmA) {
+    constexpr int H = S / 2;
+    const int step = cand >= NMODE, mode = cand - step * NMODE;
+    Bac<false> b = make_bac<false>(sm.snap[depth], &sm.tb);
+    const CtxLane cx = {(u8*)sm.lane_ctx + 4 * cand};
+    {
+        const u32* src = (const u32*)sm.snap_ctx[depth];
+        u32* dst = sm.lane_ctx + cand;
+        for (int k = 0; k < CTXW; k++) dst[k * NCAND] = src[k];
+    }
+    const CgBuf cg = {cg_staging(sm) + cand};
+    put_split_cu(b, cx, S, 0, gtL, gtA);
+    const s16* lev = sc.glev + (size_t)cand * LEV_STRIDE;
+    put_cu(b, cx, S, step, &mode, &pmL, &pmA, cg, [&](int k, LevSrc& src, unsigned& mlo, unsigned& mhi) {
+        if (step == 0) { src.p = lev; src.pitch = S; mlo = sm.cgnz[cand][0]; mhi = sm.cgnz[cand][1]; }
+        else { src.p = lev + k * H * H; src.pitch = H; mlo = sm.cgnz[cand][k]; mhi = 0; }
+    });
+    sm.cand_bits[cand] = coder_len(b.c) - coder_len(sm.snap[depth]);
+    cand_coder(sm)[cand] = b.c;
+}
+
+// NxN PU candidate: residual coding alone from a fresh coder and fresh contexts (HEVCe.c:1505-1519)
+HEVCE_HD inline void pu_cabac(Shared& sm, const Scratch& sc, int cand, int mode) {
     Bac<false> b;
     coder_reset(b.c);
     b.out = nullptr; b.cap = 0; b.tb = &sm.tb;
-    const CtxLane cx = {(u8*)sm.lane_ctx + 4 * item};
-    for (int i = 0; i < NCTX; i++) cx[i] = sm.ctx0[i];
-    put_residual(b, cx, 4, mode, [&](int y, int x) -> int { return lm.l(y * 4 + x); });
-    sm.cand_cost[item] = rd_cost(rk, sse, coder_len(b.c));
-    sm.cand_cbf[item] = nzf;
+    const CtxLane cx = {(u8*)sm.lane_ctx + 4 * cand};
+    {
+        const u32* src = (const u32*)sm.ctx0;
+        u32* dst = sm.lane_ctx + cand;
+        for (int k = 0; k < CTXW; k++) dst[k * NCAND] = src[k];
+    }
+    const CgBuf cg = {cg_staging(sm) + cand};
+    const LevSrc src = {sc.glev + (size_t)cand * LEV_STRIDE, 4};
+    put_residual(b, cx, 4, mode, src, sm.cgnz[cand][0], 0u, cg);
+    sm.cand_bits[cand] = coder_len(b.c);
 }
 
 // Evaluate the non-split candidates of one CU node and adopt the winner (HEVCe.c:1420-1559).
-// split_cost: RD cost of the already-coded split alternative (IMAX for 8x8 nodes).
 template <int S>
 HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int x0, const Avail& av, int depth) {
-    constexpr int H = S / 2, N4 = S / 4;
-    constexpr int NSTEP = S == 8 ? 3 : 2;
+    typedef Plan<S> P;
+    constexpr int H = S / 2, N4 = S / 4, NSTEP = S == 8 ? 3 : 2;
+    const RdK rk = rd_consts(q);
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
     const int gtL = S > sm.msz[my * 9 + mx - 1], gtA = S > sm.msz[(my - 1) * 9 + mx];
     const int pmL = sm.mpm[my * 9 + mx - 1], pmA = sm.mpm[(my - 1) * 9 + mx];
+    u8* pool = sm.pool;
 
     // split alternative: distortion of what the children left in the window (HEVCe.c:1409-1410)
     if (S > 8) {
@@ -807,49 +990,101 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
             for (int x = 0; x < S; x++) { const int d = (int)sm.orig[(y0 + row) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + row, x0 + x); acc += d * d; }
             sm.part_sse[row] = acc;
         }
+    }
+
+    for (int r = 0; r < P::ROUNDS; r++) {
+        const int k = r & 3;              // sub-TU / PU index of this round
+        const int chunk = r >> 2;         // 32x32 nodes only: chunk of four-TU modes
+        // ---- group descriptors (uniform)
+        Grp g0, g1, g2;
+        {   // one-TU candidates: a slice of the 35 modes per round
+            int m0, n;
+            if (S == 8) { m0 = 0; n = r == 0 ? 35 : 0; }
+            else { m0 = r * P::N0; n = imax(0, imin(P::N0, NMODE - m0)); }
+            g0.n = n; g0.cand0 = m0; g0.mode0 = m0; g0.ty = y0; g0.tx = x0; g0.av = av; g0.priv = 0;
+            g0.cuy = y0; g0.cux = x0; g0.cus = S; g0.tu = 0; g0.one_tu = 1; g0.grec = 1;
+            g0.blk = (s16*)(pool + P::BLK0); g0.pred = pool + P::PRED0; g0.psum = (int*)(pool + P::PSUM0); g0.bord = pool + P::BORD0;
+            g0.rec = nullptr; g0.rec_stride = 0; g0.rec_pitch = 0;
+        }
+        {   // four-TU candidates: sub-TU k of a chunk of modes, each with its own reconstruction as neighbour
+            const int m0 = chunk * P::N1, n = imax(0, imin(P::N1, NMODE - m0));
+            g1.n = n; g1.cand0 = NMODE + m0; g1.mode0 = m0; g1.ty = y0 + (k >> 1) * H; g1.tx = x0 + (k & 1) * H; g1.av = sub_avail(av, k); g1.priv = 1;
+            g1.cuy = y0; g1.cux = x0; g1.cus = S; g1.tu = k; g1.one_tu = 0; g1.grec = 1;
+            g1.blk = (s16*)(pool + P::BLK1); g1.pred = pool + P::PRED1; g1.psum = (int*)(pool + P::PSUM1); g1.bord = pool + P::BORD1;
+            g1.rec = pool + P::REC1; g1.rec_stride = S * S; g1.rec_pitch = S;
+        }
+        g2.n = 0;
+        if (S == 8) {   // NxN PU k: all 35 modes, neighbours from the window (earlier PUs' winners are already there)
+            g2.n = 35; g2.cand0 = 2 * NMODE; g2.mode0 = 0; g2.ty = y0 + (k >> 1) * 4; g2.tx = x0 + (k & 1) * 4; g2.av = sub_avail(av, k); g2.priv = 0;
+            g2.cuy = g2.ty; g2.cux = g2.tx; g2.cus = 4; g2.tu = 0; g2.one_tu = 0; g2.grec = 0;
+            g2.blk = (s16*)(pool + P::BLK2); g2.pred = pool + P::PRED2; g2.psum = (int*)(pool + P::PSUM2); g2.bord = pool + P::BORD2;
+            g2.rec = pool + P::REC2; g2.rec_stride = 16; g2.rec_pitch = 4;
+        }
+        const int i0 = g0.n * S, i1 = g1.n * H, i2 = g2.n * 4;
+        // ---- phase 0: reference samples
+        run_borders<S>(sm, g0, 0);
+        run_borders<H>(sm, g1, 2 * (4 * S + 1));
+        if (S == 8) run_borders<4>(sm, g2, 2 * (4 * S + 1) + g1.n * (4 * H + 1));
         PHASE_END();
-    }
-    // all one-TU / four-TU candidates (+ NxN PU round 0)
-    PAR_FOR(item, NSTEP * NMODE) {
-        int step, mode;
-        lane_decode(NSTEP, item, step, mode);
-        if (step < 2) trial_lane<S>(sm, sc, q, item, step, mode, y0, x0, av, depth, gtL, gtA, pmL, pmA);
-        else pu_lane(sm, sc, q, item, mode, y0, x0, av, 0);
-    }
-    PHASE_END();
-    if (S == 8) {
-        for (int k = 0; k < 4; k++) {
-            if (k > 0) {
-                PAR_FOR(item, NSTEP * NMODE) {
-                    int step, mode;
-                    lane_decode(NSTEP, item, step, mode);
-                    if (step == 2) pu_lane(sm, sc, q, item, mode, y0, x0, av, k);
-                }
-                PHASE_END();
+        // ---- phase A
+        PAR_FOR_OFF(item, i0, 0) phase_a_item<S>(sm, g0, item);
+        PAR_FOR_OFF(item, i1, i0) phase_a_item<H>(sm, g1, item);
+        if (S == 8) { PAR_FOR_OFF(item, i2, i0 + i1) phase_a_item<4>(sm, g2, item); }
+        PHASE_END();
+        // ---- phase B
+        PAR_FOR_OFF(item, i0, 0) phase_b_item<S>(sm, g0, item, q, rk);
+        PAR_FOR_OFF(item, i1, i0) phase_b_item<H>(sm, g1, item, q, rk);
+        if (S == 8) { PAR_FOR_OFF(item, i2, i0 + i1) phase_b_item<4>(sm, g2, item, q, rk); }
+        PHASE_END();
+        // ---- phase C
+        PAR_FOR_OFF(item, i0, 0) phase_c_item<S>(sm, sc, g0, item, q);
+        PAR_FOR_OFF(item, i1, i0) phase_c_item<H>(sm, sc, g1, item, q);
+        if (S == 8) { PAR_FOR_OFF(item, i2, i0 + i1) phase_c_item<4>(sm, sc, g2, item, q); }
+        PHASE_END();
+        // ---- phase D (+ the trial coders that only need the levels of phase C)
+        PAR_FOR_OFF(item, i0, 0) phase_d_item<S>(sm, sc, g0, item);
+        PAR_FOR_OFF(item, i1, i0) phase_d_item<H>(sm, sc, g1, item);
+        if (S == 8) {
+            PAR_FOR_OFF(item, i2, i0 + i1) phase_d_item<4>(sm, sc, g2, item);
+            PAR_FOR(t, NT) {
+                const int cand = lane_to_cand(NSTEP, t);
+                if (cand >= 2 * NMODE) pu_cabac(sm, sc, cand, cand - 2 * NMODE);
+                else if (cand >= 0 && r == 3) trial_cabac<S>(sm, sc, cand, depth, gtL, gtA, pmL, pmA);
             }
+        }
+        PHASE_END();
+        if (S == 8) {
             PAR_FOR(one, 1) {   // best PU mode, last minimum wins (HEVCe.c:1521)
                 int best = IMAX, bm = 0;
                 for (int m = 0; m < NMODE; m++) {
-                    const int c = sm.cand_cost[lane_item(NSTEP, 2, m)];
+                    const int c = rd_cost(rk, sm.cand_sse[2 * NMODE + m], sm.cand_bits[2 * NMODE + m]);
                     if (best >= c) { best = c; bm = m; }
                 }
-                const int it = lane_item(NSTEP, 2, bm);
-                const LaneMem lm = lane_mem(sc, it);
-                const int oy = (k >> 1) * 4, ox = (k & 1) * 4;
+                const int ci = 2 * NMODE + bm;
                 sm.nxn_pm[k] = bm;
-                if (k == 0) sm.nxn_cbf = 0;
-                sm.nxn_cbf |= sm.cand_cbf[it] << k;
+                sm.nxn_nz[k] = sm.cgnz[ci][0];
+                const s16* lp = sc.glev + (size_t)ci * LEV_STRIDE;
                 for (int i = 0; i < 16; i++) {
-                    sm.nxn_lev[k][i] = lm.l(i);
-                    HEVCE_WIN(sm, y0 + oy + (i >> 2), x0 + ox + (i & 3)) = lm.r(i);
+                    sm.nxn_lev[k][i] = lp[i];
+                    HEVCE_WIN(sm, g2.ty + (i >> 2), g2.tx + (i & 3)) = g2.rec[bm * 16 + i];
                 }
             }
             PHASE_END();
         }
-        PAR_FOR(one, 1) {   // the NxN CU as a whole, from the node snapshot (HEVCe.c:1531-1544)
-            Bac<false> b;
-            b.c = sm.snap[depth];
-            b.out = nullptr; b.cap = 0; b.tb = &sm.tb;
+    }
+
+    if (S > 8) {   // all 70 trial coders of a 16x16 / 32x32 node
+        PAR_FOR(t, NT) {
+            const int cand = lane_to_cand(NSTEP, t);
+            if (cand >= 0) trial_cabac<S>(sm, sc, cand, depth, gtL, gtA, pmL, pmA);
+        }
+        PHASE_END();
+    }
+
+    // ---- NxN as a whole + decision, reference order; every comparison is ">=" so the last minimum wins
+    PAR_FOR(one, 1) {
+        if (S == 8) {   // HEVCe.c:1531-1544
+            Bac<false> b = make_bac<false>(sm.snap[depth], &sm.tb);
             const CtxFlat cx = {sm.nxn_ctx};
             for (int i = 0; i < NCTX; i++) cx[i] = sm.snap_ctx[depth][i];
             int pl[4], pa[4], pm[4];
@@ -858,37 +1093,35 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
             pl[1] = pm[0]; pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
             pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; pa[2] = pm[0];
             pl[3] = pm[2]; pa[3] = pm[1];
+            const CgBuf cg = {cg_staging(sm)};
             put_split_cu(b, cx, S, 0, gtL, gtA);
-            put_cu(b, cx, S, 2, pm, pl, pa, sm.nxn_cbf, [&](int k, int y, int x) -> int { return sm.nxn_lev[k][y * 4 + x]; });
+            put_cu(b, cx, S, 2, pm, pl, pa, cg, [&](int k, LevSrc& src, unsigned& mlo, unsigned& mhi) {
+                src.p = sm.nxn_lev[k]; src.pitch = 4; mlo = sm.nxn_nz[k]; mhi = 0;
+            });
             int sse = 0;
             for (int y = 0; y < 8; y++)
                 for (int x = 0; x < 8; x++) { const int d = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += d * d; }
-            sm.nxn_cost = rd_cost(rd_consts(q), sse, coder_len(b.c) - coder_len(sm.snap[depth]));
+            sm.nxn_cost = rd_cost(rk, sse, coder_len(b.c) - coder_len(sm.snap[depth]));
             sm.nxn_coder = b.c;
         }
-        PHASE_END();
-    }
-    // decision: reference order, every comparison is ">=" so the last minimum wins (HEVCe.c:1440, 1476, 1546)
-    PAR_FOR(one, 1) {
         int best = IMAX, win = -1;
         if (S > 8) {
             int sse = 0;
             for (int r = 0; r < S; r++) sse += sm.part_sse[r];
-            best = rd_cost(rd_consts(q), sse, coder_len(sm.live) - coder_len(sm.snap[depth]));
+            best = rd_cost(rk, sse, coder_len(sm.live) - coder_len(sm.snap[depth]));
         }
-        for (int step = 0; step < 2; step++)
-            for (int m = 0; m < NMODE; m++) {
-                const int it = lane_item(NSTEP, step, m);
-                if (best >= sm.cand_cost[it]) { best = sm.cand_cost[it]; win = it; }
-            }
-        if (S == 8 && best >= sm.nxn_cost) win = NL;
+        for (int c = 0; c < 2 * NMODE; c++) {   // one-TU modes 0..34, then four-TU modes 0..34 (HEVCe.c:1440, 1476)
+            const int cost = rd_cost(rk, sm.cand_sse[c], sm.cand_bits[c]);
+            if (best >= cost) { best = cost; win = c; }
+        }
+        if (S == 8 && best >= sm.nxn_cost) win = NCAND;   // HEVCe.c:1546
         sm.win_item = win;
     }
     PHASE_END();
     const int win = sm.win_item;
     if (win < 0) return;   // the split stays: live state, window, levels and maps are already the children's
-    // adoption
-    if (win == NL) {
+    // ---- adoption
+    if (win == NCAND) {
         PAR_FOR(i, 64) {
             const int k = i >> 4, j = i & 15, oy = (k >> 1) * 4, ox = (k & 1) * 4;
             sc.ctu_lev[(y0 + oy + (j >> 2)) * CTU + x0 + ox + (j & 3)] = sm.nxn_lev[k][j];
@@ -896,23 +1129,23 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
         PAR_FOR(i, NCTX) sm.live_ctx[i] = sm.nxn_ctx[i];
         PAR_FOR(one, 1) {
             sm.live = sm.nxn_coder;
-            sm.kind[(y0 >> 3) * 4 + (x0 >> 3)] = (u8)(2 | (sm.nxn_cbf << 4));
+            sm.kind[(y0 >> 3) * 4 + (x0 >> 3)] = 2;
             for (int k = 0; k < 4; k++) {
                 sm.msz[(my + (k >> 1)) * 9 + mx + (k & 1)] = 8;
                 sm.mpm[(my + (k >> 1)) * 9 + mx + (k & 1)] = (u8)sm.nxn_pm[k];
             }
         }
     } else {
-        int step, mode;
-        lane_decode(NSTEP, win, step, mode);
-        const LaneMem lm = lane_mem(sc, win);
+        const int step = win >= NMODE, mode = win - step * NMODE;
+        const u8* rp = sc.grec + (size_t)win * (CTU * CTU);
+        const s16* lp = sc.glev + (size_t)win * LEV_STRIDE;
         PAR_FOR(i, S * S) {
             const int y = i / S, x = i % S;
-            HEVCE_WIN(sm, y0 + y, x0 + x) = lm.r(i);
+            HEVCE_WIN(sm, y0 + y, x0 + x) = rp[i];
             int li;
             if (step == 0) li = i;
             else { const int k = (y >= H) * 2 + (x >= H); li = k * H * H + (y % H) * H + (x % H); }
-            sc.ctu_lev[(y0 + y) * CTU + x0 + x] = lm.l(li);
+            sc.ctu_lev[(y0 + y) * CTU + x0 + x] = lp[li];
         }
         const CtxLane cx = {(u8*)sm.lane_ctx + 4 * win};
         PAR_FOR(i, NCTX) sm.live_ctx[i] = cx[i];
@@ -921,11 +1154,11 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
             sm.msz[idx] = (u8)S;
             sm.mpm[idx] = (u8)mode;
         }
-        PAR_FOR(i, (S >= 8 ? (S / 8) * (S / 8) : 1)) {
+        PAR_FOR(i, (S / 8) * (S / 8)) {
             const int n8 = S / 8;
-            sm.kind[((y0 >> 3) + i / n8) * 4 + (x0 >> 3) + i % n8] = (u8)(step | (sm.cand_cbf[win] << 4));
+            sm.kind[((y0 >> 3) + i / n8) * 4 + (x0 >> 3) + i % n8] = (u8)step;
         }
-        PAR_FOR(one, 1) sm.live = sm.cand_coder[win];
+        PAR_FOR(one, 1) sm.live = cand_coder(sm)[win];
     }
     PHASE_END();
 }
@@ -933,14 +1166,13 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
 // enter a node: snapshot the live state (HEVCe.c:1364-1365) and, for splittable nodes, code split_cu_flag = 1
 template <int S>
 HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
-    PAR_FOR(i, NCTX) sm.snap_ctx[depth][i] = sm.live_ctx[i];
+    PAR_FOR(i, CTXW) ((u32*)sm.snap_ctx[depth])[i] = ((const u32*)sm.live_ctx)[i];
     PAR_FOR(one, 1) sm.snap[depth] = sm.live;
     PHASE_END();
     if (S > 8) {
         PAR_FOR(one, 1) {
             const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
-            Bac<false> b;
-            b.c = sm.live; b.out = nullptr; b.cap = 0; b.tb = &sm.tb;
+            Bac<false> b = make_bac<false>(sm.live, &sm.tb);
             const CtxFlat cx = {sm.live_ctx};
             put_split_cu(b, cx, S, 1, S > sm.msz[my * 9 + mx - 1], S > sm.msz[(my - 1) * 9 + mx]);
             sm.live = b.c;
@@ -950,9 +1182,9 @@ HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
 }
 
 // re-encode the decided CTU with the byte-writing coder (replaces the reference's per-trial byte buffers)
-HEVCE_HD inline void commit_cu(Bac<true>& b, const CtxFlat& cx, const Shared& sm, const s16* lev, int s, int y0, int x0) {
+HEVCE_HD inline void commit_cu(Bac<true>& b, const CtxFlat& cx, const Shared& sm, const CgBuf& cg, const s16* lev, int s, int y0, int x0) {
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4, h = s / 2;
-    const int kd = sm.kind[(y0 >> 3) * 4 + (x0 >> 3)], kind = kd & 3, cbf = kd >> 4;
+    const int kind = sm.kind[(y0 >> 3) * 4 + (x0 >> 3)];
     int pm[4], pl[4], pa[4];
     pm[0] = sm.mpm[my * 9 + mx];
     pl[0] = sm.mpm[my * 9 + mx - 1];
@@ -963,17 +1195,19 @@ HEVCE_HD inline void commit_cu(Bac<true>& b, const CtxFlat& cx, const Shared& sm
         pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; pa[2] = pm[0];
         pl[3] = pm[2]; pa[3] = pm[1];
     }
-    put_cu(b, cx, s, kind, pm, pl, pa, cbf, [&](int k, int y, int x) -> int {
+    put_cu(b, cx, s, kind, pm, pl, pa, cg, [&](int k, LevSrc& src, unsigned& mlo, unsigned& mhi) {
         const int oy = kind == 0 ? 0 : (k >> 1) * h, ox = kind == 0 ? 0 : (k & 1) * h;
-        return lev[(y0 + oy + y) * CTU + x0 + ox + x];
+        src.p = lev + (y0 + oy) * CTU + x0 + ox;
+        src.pitch = CTU;
+        scan_groups(src, kind == 0 ? s : h, mlo, mhi);
     });
 }
 
-HEVCE_HD inline void commit_ctu(Bac<true>& b, const CtxFlat& cx, const Shared& sm, const s16* lev) {
+HEVCE_HD inline void commit_ctu(Bac<true>& b, const CtxFlat& cx, const Shared& sm, const CgBuf& cg, const s16* lev) {
     auto gt = [&](int s, int y, int x, int dy, int dx) { return s > sm.msz[(1 + y / 4 + dy) * 9 + 1 + x / 4 + dx]; };
     if (sm.msz[10] == 32) {
         put_split_cu(b, cx, 32, 0, gt(32, 0, 0, 0, -1), gt(32, 0, 0, -1, 0));
-        commit_cu(b, cx, sm, lev, 32, 0, 0);
+        commit_cu(b, cx, sm, cg, lev, 32, 0, 0);
         return;
     }
     put_split_cu(b, cx, 32, 1, gt(32, 0, 0, 0, -1), gt(32, 0, 0, -1, 0));
@@ -981,8 +1215,8 @@ HEVCE_HD inline void commit_ctu(Bac<true>& b, const CtxFlat& cx, const Shared& s
         const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
         const int sz = sm.msz[(1 + y16 / 4) * 9 + 1 + x16 / 4];
         put_split_cu(b, cx, 16, sz != 16, gt(16, y16, x16, 0, -1), gt(16, y16, x16, -1, 0));
-        if (sz == 16) { commit_cu(b, cx, sm, lev, 16, y16, x16); continue; }
-        for (int c = 0; c < 4; c++) commit_cu(b, cx, sm, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
+        if (sz == 16) { commit_cu(b, cx, sm, cg, lev, 16, y16, x16); continue; }
+        for (int c = 0; c < 4; c++) commit_cu(b, cx, sm, cg, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
     }
 }
 
@@ -996,8 +1230,7 @@ HEVCE_HD inline int write_header(u8* out, int q, int H, int W) {
     int n = 0;
     for (int i = 0; i < 27; i++) out[n++] = VPS[i];
     for (int i = 0; i < 22; i++) out[n++] = SPS[i];
-    // bit writer, MSB first
-    unsigned long long acc = 0;
+    unsigned long long acc = 0;   // bit writer, MSB first
     int nb = 0;
     auto put = [&](unsigned v, int len) {
         for (int i = len - 1; i >= 0; i--) {
@@ -1029,7 +1262,6 @@ HEVCE_HD inline int write_header(u8* out, int q, int H, int W) {
 // ------------------------------------------------------------------------------------------------------------
 HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared& sm, const Scratch& sc) {
     const int q = job.q, H = job.H, W = job.W;
-    // tables + initial state
     PAR_FOR(i, (int)sizeof(Tables)) ((u8*)&sm.tb)[i] = ((const u8*)&tables)[i];
     PHASE_END();
     PAR_FOR(i, 144) {
@@ -1062,7 +1294,7 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
                 sm.msz[(i + 1) * 9] = cx > 0 ? sm.msz[(i + 1) * 9 + 8] : (u8)CTU;      // left column = previous CTU's last column
                 sm.mpm[(i + 1) * 9] = cx > 0 ? sm.mpm[(i + 1) * 9 + 8] : (u8)1;
             }
-            PAR_FOR(i, NCTX) sm.start_ctx[i] = sm.live_ctx[i];
+            PAR_FOR(i, CTXW) ((u32*)sm.start_ctx)[i] = ((const u32*)sm.live_ctx)[i];
             PAR_FOR(one, 1) { sm.live.n = 0; sm.start = sm.live; }
             PHASE_END();
 
@@ -1086,8 +1318,7 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
             PAR_FOR(i, 8) sc.msz_line[cx / 4 + i] = sm.msz[8 * 9 + 1 + i];
             PAR_FOR(one, 1) {
                 const int last = cy + CTU >= H && cx + CTU >= W;
-                Bac<false> t;
-                t.c = sm.live; t.out = nullptr; t.cap = 0; t.tb = &sm.tb;
+                Bac<false> t = make_bac<false>(sm.live, &sm.tb);
                 t.put_terminate(last);                                                  // HEVCe.c:1630
                 if (last) t.finish();                                                   // HEVCe.c:1640
                 Bac<true> b;
@@ -1095,7 +1326,8 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
                 b.out = job.out + sm.stream_pos;
                 b.cap = imax(0, job.out_cap - sm.stream_pos);
                 const CtxFlat cxs = {sm.start_ctx};
-                commit_ctu(b, cxs, sm, sc.ctu_lev);
+                const CgBuf cg = {cg_staging(sm)};
+                commit_ctu(b, cxs, sm, cg, sc.ctu_lev);
                 b.put_terminate(last);
                 if (last) b.finish();
                 if (!coder_equal(b.c, t.c)) sm.error |= ERR_COMMIT_MISMATCH;

@@ -36,9 +36,10 @@ using namespace hevce;
 // ------------------------------------------------------------------------------------------------------------
 __device__ Tables g_tables;
 
-__global__ void __launch_bounds__(NL, 4)
+__global__ void __launch_bounds__(NT, 4)
 hevce_encode_kernel(const Job* __restrict__ jobs, const int* __restrict__ order, int njobs, const Scratch* __restrict__ slots, int* counter) {
-    __shared__ Shared sm;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared& sm = *reinterpret_cast<Shared*>(smem_raw);
     __shared__ int s_next;
     const Scratch sc = slots[blockIdx.x];
     for (;;) {
@@ -98,7 +99,8 @@ int device_prepare(int device) {
     fill_tables(host_tables);
     CK(cudaMemcpyToSymbol(g_tables, &host_tables, sizeof(Tables)));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevce_encode_kernel, NL, 0));
+    CK(cudaFuncSetAttribute(hevce_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevce_encode_kernel, NT, sizeof(Shared)));
     if (occ < 1) occ = 1;
     g_dev[device].sms = prop.multiProcessorCount;
     g_dev[device].ctas_per_sm = occ;
@@ -138,8 +140,8 @@ struct hevce_session {
     int* d_results = nullptr; size_t c_results = 0;
     int* d_counter = nullptr;
     Scratch* d_slots = nullptr; size_t c_slots = 0;
-    s16 *d_W = nullptr, *d_L = nullptr, *d_lev = nullptr; u8 *d_P = nullptr, *d_R = nullptr, *d_line = nullptr;
-    size_t c_W = 0, c_L = 0, c_lev = 0, c_P = 0, c_R = 0, c_line = 0;
+    s16 *d_glev = nullptr, *d_lev = nullptr; u8 *d_grec = nullptr, *d_line = nullptr;
+    size_t c_glev = 0, c_lev = 0, c_grec = 0, c_line = 0;
     int line_pitch = 0;
     // pinned staging
     u8* h_stage = nullptr; size_t c_stage = 0;
@@ -191,19 +193,17 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     if ((rc = grow(&s->d_order, &s->c_order, (size_t)n))) return rc;
     if ((rc = grow(&s->d_results, &s->c_results, (size_t)2 * n))) return rc;
     if (!s->d_counter) CK(cudaMalloc((void**)&s->d_counter, sizeof(int)));
-    const size_t g = (size_t)s->grid, lane = (size_t)NL * LANE_ELEMS;
+    const size_t g = (size_t)s->grid, nlev = (size_t)NCAND * LEV_STRIDE + 64, nrec = (size_t)NREC * CTU * CTU;
     s->line_pitch = maxW / 4 + 32;
-    if ((rc = grow(&s->d_W, &s->c_W, g * lane))) return rc;
-    if ((rc = grow(&s->d_L, &s->c_L, g * lane))) return rc;
-    if ((rc = grow(&s->d_P, &s->c_P, g * lane))) return rc;
-    if ((rc = grow(&s->d_R, &s->c_R, g * lane))) return rc;
+    if ((rc = grow(&s->d_glev, &s->c_glev, g * nlev))) return rc;
+    if ((rc = grow(&s->d_grec, &s->c_grec, g * nrec))) return rc;
     if ((rc = grow(&s->d_lev, &s->c_lev, g * CTU * CTU))) return rc;
     if ((rc = grow(&s->d_line, &s->c_line, g * (size_t)s->line_pitch))) return rc;
     if ((rc = grow(&s->d_slots, &s->c_slots, g))) return rc;
     std::vector<Scratch> slots(g);
     for (size_t k = 0; k < g; k++) {
-        slots[k].W = s->d_W + k * lane; slots[k].L = s->d_L + k * lane;
-        slots[k].P = s->d_P + k * lane; slots[k].R = s->d_R + k * lane;
+        slots[k].glev = s->d_glev + k * nlev;
+        slots[k].grec = s->d_grec + k * nrec;
         slots[k].ctu_lev = s->d_lev + k * CTU * CTU;
         slots[k].msz_line = s->d_line + k * (size_t)s->line_pitch;
     }
@@ -264,7 +264,7 @@ extern "C" int hevce_session_encode(hevce_session* s) {
     if (s->n == 0) return 0;
     CK(cudaMemsetAsync(s->d_counter, 0, sizeof(int), s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
-    hevce_encode_kernel<<<s->grid, NL, 0, s->stream>>>(s->d_jobs, s->d_order, s->n, s->d_slots, s->d_counter);
+    hevce_encode_kernel<<<s->grid, NT, sizeof(Shared), s->stream>>>(s->d_jobs, s->d_order, s->n, s->d_slots, s->d_counter);
     CK(cudaGetLastError());
     CK(cudaEventRecord(s->ev1, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -329,8 +329,8 @@ extern "C" void hevce_session_destroy(hevce_session* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaFree(s->d_img); cudaFree(s->d_rcon); cudaFree(s->d_out); cudaFree(s->d_jobs); cudaFree(s->d_order);
-    cudaFree(s->d_results); cudaFree(s->d_counter); cudaFree(s->d_slots); cudaFree(s->d_W); cudaFree(s->d_L);
-    cudaFree(s->d_P); cudaFree(s->d_R); cudaFree(s->d_lev); cudaFree(s->d_line);
+    cudaFree(s->d_results); cudaFree(s->d_counter); cudaFree(s->d_slots); cudaFree(s->d_glev); cudaFree(s->d_grec);
+    cudaFree(s->d_lev); cudaFree(s->d_line);
     if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);

@@ -23,10 +23,10 @@ extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned 
     job.H = (imin(*ysz, max_dim) + CTU - 1) / CTU * CTU;
     job.W = (imin(*xsz, max_dim) + CTU - 1) / CTU * CTU;
     job.q = q; job.out_cap = out_cap;
-    std::vector<s16> W(NL * LANE_ELEMS), L(NL * LANE_ELEMS), lev(CTU * CTU);
-    std::vector<u8> P(NL * LANE_ELEMS), R(NL * LANE_ELEMS), line(job.W / 4 + 8);
+    std::vector<s16> glev((size_t)NCAND * LEV_STRIDE + 16), lev(CTU * CTU);
+    std::vector<u8> grec((size_t)NREC * CTU * CTU), line(job.W / 4 + 8);
     Scratch sc;
-    sc.W = W.data(); sc.L = L.data(); sc.P = P.data(); sc.R = R.data(); sc.ctu_lev = lev.data(); sc.msz_line = line.data();
+    sc.glev = glev.data(); sc.grec = grec.data(); sc.ctu_lev = lev.data(); sc.msz_line = line.data();
     Shared* sm = new Shared;
     memset(sm, 0xA5, sizeof(Shared));   // shared memory is not zeroed on the GPU either
     encode_picture(job, tables, *sm, sc);
