@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define HEVCE_HD __host__ __device__
+#define HEVCE_NOINLINE __noinline__
 #else
 #define HEVCE_HD
+#define HEVCE_NOINLINE __attribute__((noinline))
 #endif
 
 namespace hevce {
@@ -76,6 +78,9 @@ struct Tables {
     u8 next_lps[128];      // (state<<1|mps) after an LPS                   (HEVCe.c:702)
     u8 ctx_iv[144];        // context init values by byte offset            (HEVCe.c:763-777)
     u8 scan4[3][16];       // in-CG scan, (y<<2)|x : diag / horizontal / vertical
+    u8 inv4[3][16];        // inverse: raster index (y<<2)|x -> scan index
+    u32 sigoff[3][4];      // sig_coeff ctx offset (2 bits per scan index) by neighbour pattern (HEVCe.c:1116-1121)
+    unsigned long long sig4[3];   // sig_coeff ctx of 4x4 TUs (4 bits per scan index)
     u8 cgdiag[3][64];      // diagonal CG order for 2x2 / 4x4 / 8x8 CG grids, (cy<<3)|cx
     u8 sigp4[16];          // sig_coeff ctx for 4x4 TUs                     (HEVCe.c:1093)
     u8 grp[32];            // last-position group index                     (HEVCe.c:1047)
@@ -127,6 +132,24 @@ inline void fill_tables(Tables& t) {
         else if (type == 2) { for (int x = 0; x < 4; x++) for (int y = 0; y < 4; y++) t.scan4[type][n++] = (u8)((y << 2) | x); }
         else for (int d = 0; d < 7; d++) for (int y = d < 3 ? d : 3; y >= 0; y--) { int x = d - y; if (x < 4) t.scan4[type][n++] = (u8)((y << 2) | x); }
     }
+    for (int type = 0; type < 3; type++) {
+        t.sig4[type] = 0;
+        for (int k = 0; k < 16; k++) {
+            const int p4 = t.scan4[type][k], py = p4 >> 2, px = p4 & 3;
+            t.inv4[type][p4] = (u8)k;
+            t.sig4[type] |= (unsigned long long)P4[p4] << (4 * k);
+        }
+        for (int pat = 0; pat < 4; pat++) {
+            u32 w = 0;
+            for (int k = 0; k < 16; k++) {
+                const int p4 = t.scan4[type][k], py = p4 >> 2, px = p4 & 3;
+                const int tt = pat == 0 ? py + px : pat == 1 ? 2 * py : 2 * px;
+                const u32 off = pat == 3 ? 2u : (tt == 0 ? 2u : tt < 3 ? 1u : 0u);
+                w |= off << (2 * k);
+            }
+            t.sigoff[type][pat] = w;
+        }
+    }
     for (int g = 0; g < 3; g++) {
         int ncg = 2 << g, n = 0;
         for (int i = 0; i < 64; i++) t.cgdiag[g][i] = 0;
@@ -164,8 +187,8 @@ HEVCE_HD inline int rd_cost(const RdK& k, int dist, int bits) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// arithmetic coder (HEVCe.c:797-933).  The trial variant (EMIT=false) keeps the full integer state -- including
-// the emulation-prevention bookkeeping that can change the byte count -- but stores no bytes.
+// arithmetic coder (HEVCe.c:797-933).  One coder type serves trials (out == nullptr: full integer state including
+// the emulation-prevention bookkeeping that can change the byte count, but no byte store) and the commit pass.
 // ------------------------------------------------------------------------------------------------------------
 struct Coder { int range, low, nbits, nbytes, held, z, n; };
 
@@ -175,26 +198,24 @@ HEVCE_HD inline bool coder_equal(const Coder& a, const Coder& b) {
     return a.range == b.range && a.low == b.low && a.nbits == b.nbits && a.nbytes == b.nbytes && a.held == b.held && a.z == b.z && a.n == b.n;
 }
 
-template <bool EMIT>
 struct Bac {
     Coder c;
-    u8* out;            // EMIT only: destination of this CTU's bytes
-    int cap;            // EMIT only: bytes available at out
+    u8* out;            // commit only: destination of this CTU's bytes (nullptr for trials)
+    int cap;            // commit only: bytes available at out
     const Tables* tb;
 
     HEVCE_HD void emit(int byte) {   // HEVCe.c:821-832
         const int b = byte & 0xff;
         if (c.z >= 2 && b <= 3) {
-            if (EMIT) { if (c.n < cap) out[c.n] = 3; }
+            if (out && c.n < cap) out[c.n] = 3;
             c.n++;
             c.z = 0;
         }
-        if (EMIT) { if (c.n < cap) out[c.n] = (u8)b; }
+        if (out && c.n < cap) out[c.n] = (u8)b;
         c.n++;
         c.z = b ? 0 : c.z + 1;
     }
-    HEVCE_HD void carry_out() {      // HEVCe.c:859-879
-        if (c.nbits >= 12) return;
+    HEVCE_HD HEVCE_NOINLINE void carry_slow() {   // HEVCe.c:861-878
         const int lead = c.low >> (24 - c.nbits);
         c.nbits += 8;
         c.low &= (int)(0xFFFFFFFFu >> c.nbits);
@@ -206,6 +227,7 @@ struct Bac {
             for (; c.nbytes > 1; c.nbytes--) emit((0xff + carry) & 0xff);
         } else { c.nbytes = 1; c.held = lead; }
     }
+    HEVCE_HD void carry_out() { if (c.nbits < 12) carry_slow(); }   // HEVCe.c:859-860
     HEVCE_HD void put_bin(int bin, u8& cx) {   // HEVCe.c:914-933
         const int v = cx;
         const int lps = tb->lps[(v >> 1) * 4 + ((c.range >> 6) & 3)];
@@ -249,14 +271,12 @@ struct Bac {
     }
 };
 
-// context-set accessors: plain array, or the lane-private word-interleaved layout in shared memory
-struct CtxFlat {
+// context set: byte k at p[(k>>2)*s4 + (k&3)].  s4 = 4: plain array; s4 = 4*NCAND: lane-private column of the
+// word-interleaved shared-memory array (every lane owns one bank).
+struct Cx {
     u8* p;
-    HEVCE_HD u8& operator[](int k) const { return p[k]; }
-};
-struct CtxLane {   // byte k of lane l lives in word (k>>2)*NCAND + l  -> every lane owns one bank
-    u8* p;         // = (u8*)lane_ctx + 4*lane
-    HEVCE_HD u8& operator[](int k) const { return p[(k >> 2) * (NCAND * 4) + (k & 3)]; }
+    int s4;
+    HEVCE_HD u8& operator[](int k) const { return p[(k >> 2) * s4 + (k & 3)]; }
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -268,121 +288,30 @@ HEVCE_HD inline void mpm_list(int l, int a, int (&m)[3]) {   // HEVCe.c:958-977
     else { m[0] = 0; m[1] = 1; m[2] = 26; }
 }
 
-template <bool E, class CX>
-HEVCE_HD inline void put_luma_modes(Bac<E>& b, const CX& cx, int n, const int* pm, const int* pl, const int* pa) {   // HEVCe.c:985-1018
-    int hit[4], mp[4][3];
-    for (int i = 0; i < n; i++) {
-        mpm_list(pl[i], pa[i], mp[i]);
-        hit[i] = -1;
-        for (int j = 0; j < 3; j++) if (mp[i][j] == pm[i]) hit[i] = j;
-        b.put_bin(hit[i] >= 0, cx[CX_YPM]);
-    }
-    for (int i = 0; i < n; i++) {
-        if (hit[i] >= 0) {
-            b.put_bypass(hit[i] > 0, 1);
-            if (hit[i] > 0) b.put_bypass(hit[i] - 1, 1);
-        } else {
-            int r = pm[i];
-            const int hi = imax(mp[i][0], imax(mp[i][1], mp[i][2])), lo = imin(mp[i][0], imin(mp[i][1], mp[i][2]));
-            const int mid = mp[i][0] + mp[i][1] + mp[i][2] - hi - lo;
-            if (r > hi) r--;
-            if (r > mid) r--;
-            if (r > lo) r--;
-            b.put_bypass(r, 5);
-        }
-    }
-}
-
 HEVCE_HD inline int scan_type(int s, int m) {   // HEVCe.c:1134-1150
     if (s <= 8) { if (iabs(m - 26) <= 4) return 1; if (iabs(m - 10) <= 4) return 2; }
     return 0;
 }
 
-// scan index -> (y<<5)|x for a TU with lg = log2(size), scan type st
-HEVCE_HD inline int scan_pos(const Tables* tb, int lg, int st, int i) {
-    const int k = tb->scan4[st][i & 15], g = i >> 4;
-    int cy, cx;
-    if (lg == 2) { cy = 0; cx = 0; }
-    else if (st == 1) { cy = g >> 1; cx = g & 1; }      // only 8x8 TUs use the non-diagonal scans
-    else if (st == 2) { cy = g & 1; cx = g >> 1; }
-    else { const int v = tb->cgdiag[lg - 3][g]; cy = v >> 3; cx = v & 7; }
-    return ((cy * 4 + (k >> 2)) << 5) | (cx * 4 + (k & 3));
+// Levels of a TU are stored group by group (groups in raster order, gy*ncg+gx), the 16 levels of a group in the
+// scan order of the candidate's mode: a trial coder fetches one group with two 16-byte loads.
+HEVCE_HD inline void load_group(const s16* p, u32 (&w)[8]) {
+#if defined(__CUDA_ARCH__)
+    const uint4 a = ((const uint4*)p)[0], b = ((const uint4*)p)[1];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) w[i] = (u32)(unsigned short)p[2 * i] | ((u32)(unsigned short)p[2 * i + 1] << 16);
+#endif
 }
 
-template <bool E, class CX>
-HEVCE_HD inline void put_last_xy(Bac<E>& b, const CX& cx, int s, int st, int y, int x) {   // HEVCe.c:1046-1087
-    const Tables* tb = b.tb;
-    const int row = ilog2(s) - 2, sh = s > 4;
-    int ty = st == 2 ? x : y, tx = st == 2 ? y : x;
-    const int gy = tb->grp[ty], gx = tb->grp[tx], gmax = tb->grp[s - 1];
-    const int bx = CX_LASTX + 5 * row, by = CX_LASTY + 5 * row;
-    for (int i = 0; i < gx; i++) b.put_bin(1, cx[bx + (i >> sh)]);
-    if (gx < gmax) b.put_bin(0, cx[bx + (gx >> sh)]);
-    for (int i = 0; i < gy; i++) b.put_bin(1, cx[by + (i >> sh)]);
-    if (gy < gmax) b.put_bin(0, cx[by + (gy >> sh)]);
-    if (gx > 3) { tx -= tb->gmin[gx]; for (int i = ((gx - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((tx >> i) & 1, 1); }
-    if (gy > 3) { ty -= tb->gmin[gy]; for (int i = ((gy - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((ty >> i) & 1, 1); }
-}
-
-HEVCE_HD inline int sig_ctx_index(const Tables* tb, int s, int st, int y, int x, int pat) {   // HEVCe.c:1092-1122, luma
-    if (!y && !x) return 0;
-    if (s == 4) return tb->sigp4[y * 4 + x];
-    int k = 9;
-    if (s >= 16) k += 12;
-    if (s == 8 && st) k += 6;
-    if ((y >> 2) || (x >> 2)) k += 3;
-    const int py = y & 3, px = x & 3;
-    int t;
-    if (pat == 0) t = py + px;
-    else if (pat == 1) t = 2 * py;
-    else if (pat == 2) t = 2 * px;
-    else return k + 2;
-    return k + (t == 0 ? 2 : t < 3 ? 1 : 0);
-}
-
-template <bool E>
-HEVCE_HD inline void put_remaining(Bac<E>& b, int v, int rp) {   // HEVCe.c:1154-1169
-    if (v < (3 << rp)) {
-        const int n = v >> rp;
-        b.put_bypass((1 << (n + 1)) - 2, n + 1);
-        b.put_bypass(v & ((1 << rp) - 1), rp);
-    } else {
-        int n = rp;
-        v -= 3 << rp;
-        for (; v >= (1 << n); n++) v -= 1 << n;
-        const int pre = 4 + n - rp;
-        b.put_bypass((1 << pre) - 2, pre);
-        b.put_bypass(v, n);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // residual_coding() of one TU (HEVCe.c:1173-1269), restructured around coefficient groups: the caller supplies the
-// bitmap of non-zero 4x4 groups (bit gy*8+gx), so all-zero groups cost one bin and no memory traffic, and the 16
-// levels of a coded group are staged once into a lane-private shared-memory column.
-// ------------------------------------------------------------------------------------------------------------
-struct LevSrc {            // raster block of levels; every row of a group (4 x s16) is 8-byte aligned
-    const s16* p;
-    int pitch;
-};
-struct CgBuf {             // lane-private staging column: level k of the group at word (k>>1)*NCAND + lane
-    u32* w;                // = cgbuf + lane
-    HEVCE_HD int at(int k) const { return ((const s16*)(w + (k >> 1) * NCAND))[k & 1]; }
-    HEVCE_HD void load(const LevSrc& s, int gy, int gx) const {
-        const s16* q = s.p + (gy * 4) * s.pitch + gx * 4;
-        for (int r = 0; r < 4; r++) {
-            const unsigned long long v = *(const unsigned long long*)(q + r * s.pitch);
-            w[(2 * r) * NCAND] = (u32)v;
-            w[(2 * r + 1) * NCAND] = (u32)(v >> 32);
-        }
-    }
-    HEVCE_HD void zero() const { for (int i = 0; i < 8; i++) w[i * NCAND] = 0; }
-};
-
-template <bool E, class CX>
-HEVCE_HD inline void put_residual(Bac<E>& b, const CX& cx, int s, int m, const LevSrc& src, unsigned mlo, unsigned mhi, const CgBuf& cg) {
+// bitmap of non-zero 4x4 groups (bit gy*8+gx), so all-zero groups cost one bin and no memory traffic; a coded group
+// is reduced to three bit-fields in scan order (non-zero mask, signs, min(|level|,3) classes) that drive every
+// context-coded bin; only escape magnitudes are read back from the store.
+HEVCE_HD HEVCE_NOINLINE void put_residual(Bac& b, const Cx cx, int s, int m, const s16* lev, unsigned mlo, unsigned mhi) {
     const Tables* tb = b.tb;
     const int st = scan_type(s, m), lg = ilog2(s), ncg = s >> 2;
+    const int sigbase = CX_SIG + 9 + (s >= 16 ? 12 : 0) + ((s == 8 && st) ? 6 : 0);
     auto cgpos = [&](int g, int& cy, int& cxg) {
         if (lg == 2) { cy = 0; cxg = 0; }
         else if (st == 1) { cy = g >> 1; cxg = g & 1; }
@@ -405,47 +334,103 @@ HEVCE_HD inline void put_residual(Bac<E>& b, const CX& cx, int s, int m, const L
         const int pat = (dwn << 1) | rgt;
         if (g != gl && !first_cg) b.put_bin(on, cx[CX_SIGCG + (pat != 0)]);
         if (!on && !first_cg) continue;
-        if (on) cg.load(src, cy, cxg); else cg.zero();
+        // ---- bit-fields of the group, scan order
+        const s16* gp = lev + (cy * ncg + cxg) * 16;
+        unsigned nzm = 0, sgn = 0, cls = 0;
+        if (on) {
+            u32 w[8];
+            load_group(gp, w);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int v = (int)(s16)(w[k >> 1] >> (16 * (k & 1)));
+                const unsigned a = (unsigned)imin(iabs(v), 3);
+                nzm |= (unsigned)(v != 0) << k;
+                sgn |= (unsigned)(v < 0) << k;
+                cls |= a << (2 * k);
+            }
+        }
         int kstart = 15;
         if (g == gl) {
-            if (on) { while (kstart > 0 && cg.at(tb->scan4[st][kstart]) == 0) kstart--; }
-            else kstart = 0;
+            kstart = nzm ? bitlen(nzm) - 1 : 0;
             const int p4 = tb->scan4[st][kstart];
-            put_last_xy(b, cx, s, st, cy * 4 + (p4 >> 2), cxg * 4 + (p4 & 3));
+            // last_sig_coeff_xy (HEVCe.c:1046-1087)
+            const int y = cy * 4 + (p4 >> 2), x = cxg * 4 + (p4 & 3);
+            const int row = lg - 2, sh = s > 4;
+            int ty = st == 2 ? x : y, tx = st == 2 ? y : x;
+            const int gy = tb->grp[ty], gx = tb->grp[tx], gmax = tb->grp[s - 1];
+            const int bx = CX_LASTX + 5 * row, by = CX_LASTY + 5 * row;
+            for (int i = 0; i < gx; i++) b.put_bin(1, cx[bx + (i >> sh)]);
+            if (gx < gmax) b.put_bin(0, cx[bx + (gx >> sh)]);
+            for (int i = 0; i < gy; i++) b.put_bin(1, cx[by + (i >> sh)]);
+            if (gy < gmax) b.put_bin(0, cx[by + (gy >> sh)]);
+            if (gx > 3) { tx -= tb->gmin[gx]; for (int i = ((gx - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((tx >> i) & 1, 1); }   // one bin per call,
+            if (gy > 3) { ty -= tb->gmin[gy]; for (int i = ((gy - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((ty >> i) & 1, 1); }   // as HEVCe.c:1076-1086
         }
-        int nz = 0, signs = 0;
-        unsigned cls = 0;   // min(|level|,3) of the non-zero levels in coding order, 2 bits each
-        for (int k = kstart; k >= 0; k--) {
-            const int p4 = tb->scan4[st][k];
-            const int v = cg.at(p4);
-            const bool is_last = g == gl && k == kstart;
-            if (!is_last && (first_cg || k > 0 || nz > 0))
-                b.put_bin(v != 0, cx[CX_SIG + sig_ctx_index(tb, s, st, cy * 4 + (p4 >> 2), cxg * 4 + (p4 & 3), pat)]);
-            if (v) {
-                cls |= (unsigned)imin(iabs(v), 3) << (2 * nz);
-                nz++;
-                signs = (signs << 1) | (v < 0);
+        // ---- sig_coeff_flags (HEVCe.c:1219-1222, context HEVCe.c:1092-1122)
+        {
+            const u32 soff = tb->sigoff[st][pat];
+            const unsigned long long s4 = tb->sig4[st];
+            const int base = sigbase + (first_cg ? 0 : 3);
+            int k = (g == gl) ? kstart - 1 : 15;
+            const int kend = (!first_cg && (nzm & ~1u) == 0) ? 1 : 0;   // position 0 of a later group is inferred when it is the only one
+            for (; k >= kend; k--) {
+                int ci;
+                if (s == 4) ci = CX_SIG + (int)((s4 >> (4 * k)) & 15u);
+                else if (first_cg && k == 0) ci = CX_SIG;
+                else ci = base + (int)((soff >> (2 * k)) & 3u);
+                b.put_bin((nzm >> k) & 1u, cx[ci]);
             }
         }
-        if (nz > 0) {
+        if (nzm) {
+            // ---- greater1 / greater2 flags, signs (HEVCe.c:1229-1252)
             const int set = (first_cg ? 0 : 2) + (c1 == 0);
-            int esc = nz > 8, g2 = -1;
+            int nz = 0, signs = 0, g2 = -1;
             c1 = 1;
-            for (int j = 0; j < 8 && j < nz; j++) {
-                const int a = (int)((cls >> (2 * j)) & 3u), big = a > 1;
-                b.put_bin(big, cx[CX_ONE + 4 * set + c1]);
-                if (big) { c1 = 0; if (g2 < 0) g2 = a > 2; else esc = 1; }
-                else if (c1 > 0 && c1 < 3) c1++;
+            unsigned mm = nzm;
+            while (mm) {
+                const int k = bitlen(mm) - 1;
+                mm &= ~(1u << k);
+                signs = (signs << 1) | (int)((sgn >> k) & 1u);
+                if (nz < 8) {
+                    const int a = (int)((cls >> (2 * k)) & 3u), big = a > 1;
+                    b.put_bin(big, cx[CX_ONE + 4 * set + c1]);
+                    if (big) { c1 = 0; if (g2 < 0) g2 = a > 2; else g2 |= 4; }
+                    else if (c1 > 0 && c1 < 3) c1++;
+                }
+                nz++;
             }
-            if (c1 == 0 && g2 >= 0) { b.put_bin(g2, cx[CX_ABS + set]); esc |= g2; }
+            int esc = nz > 8;
+            if (g2 >= 0) {
+                if (g2 & 4) esc = 1;
+                g2 &= 1;
+                if (c1 == 0) { b.put_bin(g2, cx[CX_ABS + set]); esc |= g2; }
+            }
             b.put_bypass(signs, nz);
+            // ---- coeff_abs_level_remaining (HEVCe.c:1254-1266, 1154-1169)
             if (esc) {
                 int base = 3, rp = 0, j = 0;
-                for (int k = kstart; k >= 0; k--) {
-                    const int a = iabs(cg.at(tb->scan4[st][k]));
-                    if (!a) continue;
-                    const int ev = a - (j < 8 ? base : 1);
-                    if (ev >= 0) { put_remaining(b, ev, rp); if (a > (3 << rp)) rp = imin(rp + 1, 4); }
+                mm = nzm;
+                while (mm) {
+                    const int k = bitlen(mm) - 1;
+                    mm &= ~(1u << k);
+                    int a = (int)((cls >> (2 * k)) & 3u);
+                    if (a == 3) a = iabs((int)gp[k]);
+                    int v = a - (j < 8 ? base : 1);
+                    if (v >= 0) {
+                        if (v < (3 << rp)) {
+                            const int n = v >> rp;
+                            b.put_bypass((1 << (n + 1)) - 2, n + 1);
+                            b.put_bypass(v & ((1 << rp) - 1), rp);
+                        } else {
+                            int n = rp;
+                            v -= 3 << rp;
+                            for (; v >= (1 << n); n++) v -= 1 << n;
+                            const int pre = 4 + n - rp;
+                            b.put_bypass((1 << pre) - 2, pre);
+                            b.put_bypass(v, n);
+                        }
+                        if (a > (3 << rp)) rp = imin(rp + 1, 4);
+                    }
                     if (a >= 2) base = 2;
                     j++;
                 }
@@ -454,40 +439,68 @@ HEVCE_HD inline void put_residual(Bac<E>& b, const CX& cx, int s, int m, const L
     }
 }
 
-// One CU (HEVCe.c:1272-1340).  kind 0: 2Nx2N one TU, 1: 2Nx2N four TUs, 2: NxN.
-// tu(k, src, mlo, mhi): levels + non-zero-group bitmap of TU k (k = 0 for kind 0).
-template <bool E, class CX, class TUF>
-HEVCE_HD inline void put_cu(Bac<E>& b, const CX& cx, int s, int kind, const int* pm, const int* pl, const int* pa, const CgBuf& cg, const TUF& tu) {
-    if (s == 8) b.put_bin(kind != 2, cx[CX_PART]);
-    put_luma_modes(b, cx, kind == 2 ? 4 : 1, pm, pl, pa);
-    b.put_bin(0, cx[CX_UVPM]);
-    if (kind != 2) b.put_bin(kind == 1, cx[CX_SPLIT_TU + (s == 32 ? 0 : s == 16 ? 1 : 2)]);
-    b.put_bin(0, cx[CX_UVCBF]);
-    b.put_bin(0, cx[CX_UVCBF]);
-    const int ntu = kind == 0 ? 1 : 4, ts = kind == 0 ? s : s >> 1;
+// One coding unit (HEVCe.c:1272-1340, 943-947).
+struct CuDesc {
+    int s;              // CU size
+    int kind;           // 0: 2Nx2N one TU, 1: 2Nx2N four TUs, 2: NxN, 3: residual of one TU only (NxN PU trial, HEVCe.c:1516)
+    int split_ctx;      // >= 0: code split_cu_flag = 0 with this context first (only s >= 16 codes it)
+    int pm[4], pl[4], pa[4];
+    const s16* lev[4];  // levels of TU k
+    unsigned mlo[4];    // non-zero-group bitmaps of TU k (low word); mhi: high word of TU 0 (32x32 only)
+    unsigned mhi;
+};
+
+HEVCE_HD HEVCE_NOINLINE void code_cu(Bac& b, const Cx cx, const CuDesc& d) {
+    const int s = d.s, kind = d.kind;
+    if (kind != 3) {
+        if (d.split_ctx >= 0 && s >= 16) b.put_bin(0, cx[CX_SPLIT_CU + d.split_ctx]);
+        if (s == 8) b.put_bin(kind != 2, cx[CX_PART]);
+        // luma modes (HEVCe.c:985-1018)
+        const int n = kind == 2 ? 4 : 1;
+        int hit[4], mp[4][3];
+        for (int i = 0; i < n; i++) {
+            mpm_list(d.pl[i], d.pa[i], mp[i]);
+            hit[i] = -1;
+            for (int j = 0; j < 3; j++) if (mp[i][j] == d.pm[i]) hit[i] = j;
+            b.put_bin(hit[i] >= 0, cx[CX_YPM]);
+        }
+        for (int i = 0; i < n; i++) {
+            if (hit[i] >= 0) {
+                b.put_bypass(hit[i] > 0, 1);
+                if (hit[i] > 0) b.put_bypass(hit[i] - 1, 1);
+            } else {
+                int r = d.pm[i];
+                const int hi = imax(mp[i][0], imax(mp[i][1], mp[i][2])), lo = imin(mp[i][0], imin(mp[i][1], mp[i][2]));
+                const int mid = mp[i][0] + mp[i][1] + mp[i][2] - hi - lo;
+                if (r > hi) r--;
+                if (r > mid) r--;
+                if (r > lo) r--;
+                b.put_bypass(r, 5);
+            }
+        }
+        b.put_bin(0, cx[CX_UVPM]);
+        if (kind != 2) b.put_bin(kind == 1, cx[CX_SPLIT_TU + (s == 32 ? 0 : s == 16 ? 1 : 2)]);
+        b.put_bin(0, cx[CX_UVCBF]);
+        b.put_bin(0, cx[CX_UVCBF]);
+    }
+    const int ntu = (kind == 0 || kind == 3) ? 1 : 4, ts = kind == 0 ? s : kind == 3 ? 4 : s >> 1;
     for (int k = 0; k < ntu; k++) {
-        LevSrc src;
-        unsigned mlo, mhi;
-        tu(k, src, mlo, mhi);
+        const unsigned mlo = d.mlo[k], mhi = k == 0 ? d.mhi : 0u;
         const int on = (mlo | mhi) != 0;
-        b.put_bin(on, cx[CX_YCBF + (kind == 0)]);
-        if (on) put_residual(b, cx, ts, pm[kind == 2 ? k : 0], src, mlo, mhi, cg);
+        if (kind != 3) b.put_bin(on, cx[CX_YCBF + (kind == 0)]);
+        if (on || kind == 3) put_residual(b, cx, ts, d.pm[kind == 2 ? k : 0], d.lev[k], mlo, mhi);
     }
 }
 
-template <bool E, class CX>
-HEVCE_HD inline void put_split_cu(Bac<E>& b, const CX& cx, int s, int flag, int gtL, int gtA) {   // HEVCe.c:943-947
-    if (s >= 16) b.put_bin(flag, cx[CX_SPLIT_CU + (gtL != 0) + (gtA != 0)]);
-}
-
-// bitmap of non-zero 4x4 groups of a TU (used by the commit pass; the trial path gets it from phase C)
-HEVCE_HD inline void scan_groups(const LevSrc& src, int s, unsigned& mlo, unsigned& mhi) {
+// bitmap of non-zero 4x4 groups of a stored TU (commit pass; the trial path gets it from phase C)
+HEVCE_HD inline void scan_groups(const s16* lev, int s, unsigned& mlo, unsigned& mhi) {
+    const int ncg = s >> 2;
     mlo = mhi = 0;
-    for (int gy = 0; gy < (s >> 2); gy++)
-        for (int gx = 0; gx < (s >> 2); gx++) {
-            unsigned long long any = 0;
-            for (int r = 0; r < 4; r++) any |= *(const unsigned long long*)(src.p + (gy * 4 + r) * src.pitch + gx * 4);
-            if (any) { const int k = gy * 8 + gx; if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
+    for (int gy = 0; gy < ncg; gy++)
+        for (int gx = 0; gx < ncg; gx++) {
+            u32 w[8];
+            load_group(lev + (gy * ncg + gx) * 16, w);
+            if (w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) { const int k = gy * 8 + gx; if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
         }
 }
 
@@ -536,26 +549,25 @@ constexpr int LEV_STRIDE = CTU * CTU;   // per-candidate level store (all TUs of
 constexpr int NREC = 70;                // candidates whose reconstruction is kept (one-TU + four-TU)
 
 struct Scratch {       // per picture slot, global memory (L2-resident working set)
-    s16* glev;         // [NCAND][LEV_STRIDE] final levels of every candidate of the current node
+    s16* glev;         // [NCAND][LEV_STRIDE] final levels of every candidate of the current node (group-blocked)
     u8* grec;          // [NREC][CTU*CTU] reconstruction of every non-NxN candidate, CU-local raster
-    s16* ctu_lev;      // CTU*CTU final levels of the current CTU (pitch CTU)
+    s16* ctu_lev;      // CTU*CTU final levels of the current CTU: CUs at their z-order offset, group-blocked
     u8* msz_line;      // CU-size map row of the CTU row above, W/4 entries
 };
 
 constexpr int POOL_BYTES = 29440;
-constexpr int AUX_CODER = 23552;                 // pool tail: trial-coder results + group staging (free whenever they are used)
-constexpr int AUX_CGBUF = AUX_CODER + 1968;
+constexpr int AUX_CODER = 23552;        // pool tail: trial-coder results (free whenever they are used)
 
 struct Shared {
     Tables tb;
     alignas(16) u8 pool[POOL_BYTES];    // per-node carve-up: work blocks, predictions, borders (see Plan<S>)
     u32 lane_ctx[CTXW * NCAND];         // lane-private context sets, word-interleaved
-    alignas(8) u8 ctx0[144];            // freshly initialised contexts for this picture's qpd6
-    alignas(8) u8 live_ctx[144];
-    alignas(8) u8 snap_ctx[3][144];
-    alignas(8) u8 start_ctx[144];
-    alignas(8) u8 nxn_ctx[144];
-    alignas(8) s16 nxn_lev[4][16];
+    alignas(16) u8 ctx0[144];           // freshly initialised contexts for this picture's qpd6
+    alignas(16) u8 live_ctx[144];
+    alignas(16) u8 snap_ctx[3][144];
+    alignas(16) u8 start_ctx[144];
+    alignas(16) u8 nxn_ctx[144];
+    alignas(16) s16 nxn_lev[4][16];
     u8 orig[CTU * CTU];
     u8 win[(CTU + 1) * WP];
     u8 msz[81], mpm[81];                // [1+uy][1+ux], 4x4 units; row 0 / col 0 = neighbours
@@ -563,6 +575,7 @@ struct Shared {
     Coder live, snap[3], start, nxn_coder;
     int cand_sse[NCAND], cand_bits[NCAND];
     unsigned cgnz[NCAND][4];            // non-zero-group bitmaps: one-TU: [0],[1] = low/high word; else [tu]
+    int rate6[6];                       // RDOQ: weighted rate of levels 0..5
     int nxn_pm[4], nxn_cost;
     unsigned nxn_nz[4];
     int part_sse[CTU];
@@ -572,8 +585,7 @@ struct Shared {
 };
 
 HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CODER); }
-HEVCE_HD inline u32* cg_staging(Shared& sm) { return (u32*)(sm.pool + AUX_CGBUF); }
-static_assert(AUX_CGBUF + 8 * NCAND * 4 <= POOL_BYTES, "pool tail too small");
+static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail too small");
 
 // work-item phases.  On the GPU a phase is a strided loop over the CTA's threads followed by __syncthreads();
 // in the simulator it is a loop over the items in a permuted order.
@@ -613,6 +625,12 @@ HEVCE_HD inline Avail sub_avail(const Avail& a, int k) {   // HEVCe.c:1376-1379
 // window sample relative to CTU pixel (y,x); y or x may be -1
 #define HEVCE_WIN(sm, y, x) ((sm).win[(1 + (y)) * WP + 1 + (x)])
 
+// z-order offset of the 8x8 unit at CTU position (y,x) in the CTU level store
+HEVCE_HD inline int zoff(int y, int x) {
+    const int a = y >> 3, c = x >> 3;
+    return (((a & 2) << 2) | ((c & 2) << 1) | ((a & 1) << 1) | (c & 1)) * 64;
+}
+
 // trial lanes: thread -> candidate.  Modes 0..31 of a step share a warp, the 3 leftover modes are packed behind.
 HEVCE_HD inline int lane_to_cand(int nsteps, int t) {   // returns step*35+mode, or -1
     if (t < nsteps * 32) return (t >> 5) * NMODE + (t & 31);
@@ -647,6 +665,7 @@ template <int T> struct Dim {
     static constexpr int LG = T == 4 ? 2 : T == 8 ? 3 : T == 16 ? 4 : 5;
     static constexpr int BLK = T * T + T;      // padded so that column items of neighbouring candidates hit distinct banks
     static constexpr int BS = 4 * T + 4;       // border array: [pad][2T left, bottom first][corner][2T top][pad]
+    static constexpr int UNR = T <= 8 ? T : 1; // loops that do not need register arrays stay rolled for the large sizes
 };
 
 // phase 0: reference samples (HEVCe.c:196-257) into the unified border array b[0..4T]: b[2T] = corner,
@@ -690,7 +709,7 @@ HEVCE_HD inline void border_item(Shared& sm, const Grp& g, int item) {
 // phase A: prediction of column x (HEVCe.c:262-381), residual, forward column transform (HEVCe.c:514)
 template <int T>
 HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
-    constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, BS = Dim<T>::BS;
+    constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, BS = Dim<T>::BS, UNR = Dim<T>::UNR;
     const int c = item >> LG, x = item & (T - 1), m = g.mode0 + c;
     const int bsel = g.priv ? c : (T > 4 && use_filtered(T, m));
     const u8* B = g.bord + bsel * BS + 1 + 2 * T;   // B[k]: k > 0 top[k-1], k < 0 left[-k-1], 0 corner
@@ -701,63 +720,51 @@ HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
         if (g.one_tu) { sm.cgnz[ci][0] = 0; sm.cgnz[ci][1] = 0; sm.cand_sse[ci] = 0; }
         else { sm.cgnz[ci][g.tu] = 0; if (g.tu == 0 || !g.priv) sm.cand_sse[ci] = 0; }
     }
-    int v[T], o[T];
     const bool edge = T <= 16;
     if (m == 0) {
         const int tr = B[T + 1], bl = B[-T - 1], tx = B[1 + x];
-#pragma unroll
-        for (int y = 0; y < T; y++) v[y] = ((T - 1 - x) * B[-1 - y] + (x + 1) * tr + (T - 1 - y) * tx + (y + 1) * bl + T) >> (LG + 1);
+#pragma unroll UNR
+        for (int y = 0; y < T; y++) pp[y * T] = (u8)(((T - 1 - x) * B[-1 - y] + (x + 1) * tr + (T - 1 - y) * tx + (y + 1) * bl + T) >> (LG + 1));
     } else if (m == 1) {
         int dc = T;
+#pragma unroll UNR
         for (int i = 0; i < T; i++) dc += B[-1 - i] + B[1 + i];
         dc >>= LG + 1;
-#pragma unroll
-        for (int y = 0; y < T; y++) v[y] = dc;
-        if (edge) {
-            if (x == 0) {
-#pragma unroll
-                for (int y = 1; y < T; y++) v[y] = (2 + 3 * dc + B[-1 - y]) >> 2;
-                v[0] = (2 + 2 * dc + B[-1] + B[1]) >> 2;
-            } else v[0] = (2 + 3 * dc + B[1 + x]) >> 2;
-        }
+#pragma unroll UNR
+        for (int y = 0; y < T; y++) pp[y * T] = (u8)((edge && x == 0 && y > 0) ? (2 + 3 * dc + B[-1 - y]) >> 2 : dc);
+        if (edge) pp[0] = (u8)(x == 0 ? (2 + 2 * dc + B[-1] + B[1]) >> 2 : (2 + 3 * dc + B[1 + x]) >> 2);
     } else if (m == 10) {
-#pragma unroll
-        for (int y = 0; y < T; y++) v[y] = B[-1 - y];
-        if (edge) v[0] = iclip(((B[1 + x] - B[0]) >> 1) + B[-1], 0, 255);
+#pragma unroll UNR
+        for (int y = 0; y < T; y++) pp[y * T] = B[-1 - y];
+        if (edge) pp[0] = (u8)iclip(((B[1 + x] - B[0]) >> 1) + B[-1], 0, 255);
     } else if (m == 26) {
         const int t = B[1 + x];
-#pragma unroll
-        for (int y = 0; y < T; y++) v[y] = t;
-        if (edge && x == 0) {
-#pragma unroll
-            for (int y = 0; y < T; y++) v[y] = iclip(((B[-1 - y] - B[0]) >> 1) + t, 0, 255);
-        }
+#pragma unroll UNR
+        for (int y = 0; y < T; y++) pp[y * T] = (u8)((edge && x == 0) ? iclip(((B[-1 - y] - B[0]) >> 1) + t, 0, 255) : t);
     } else {
         const int ang = intra_angle(m), aa = iabs(ang), inv = (8192 + aa / 2) / aa;   // HEVCe.c:283
         if (m < 18) {   // horizontal family: main arm = left, projected side = top
             const int off = ang * (x + 1), oi = off >> 5, of = off & 31;
             auto R = [&](int k) -> int { return k >= 0 ? B[-k] : B[(128 - inv * k) >> 8]; };
             int prev = R(oi + 1);
-#pragma unroll
+#pragma unroll UNR
             for (int y = 0; y < T; y++) {
                 const int nxt = R(oi + y + 2);
-                v[y] = ((32 - of) * prev + of * nxt + 16) >> 5;
+                pp[y * T] = (u8)(((32 - of) * prev + of * nxt + 16) >> 5);
                 prev = nxt;
             }
         } else {        // vertical family: main arm = top, projected side = left
             auto R = [&](int k) -> int { return k >= 0 ? B[k] : B[-((128 - inv * k) >> 8)]; };
-#pragma unroll
+#pragma unroll UNR
             for (int y = 0; y < T; y++) {
                 const int off = ang * (y + 1), oi = off >> 5, of = off & 31, k = oi + x + 1;
-                v[y] = ((32 - of) * R(k) + of * R(k + 1) + 16) >> 5;
+                pp[y * T] = (u8)(((32 - of) * R(k) + of * R(k + 1) + 16) >> 5);
             }
         }
     }
+    int v[T], o[T];
 #pragma unroll
-    for (int y = 0; y < T; y++) {
-        pp[y * T] = (u8)v[y];
-        v[y] = (int)org[y * CTU] - v[y];
-    }
+    for (int y = 0; y < T; y++) v[y] = (int)org[y * CTU] - (int)pp[y * T];
     Xf<T>::f(v, o);
     s16* bp = g.blk + c * BLK + x;
     constexpr int A1 = LG - 1;
@@ -766,25 +773,32 @@ HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
 }
 
 // phase B: forward row transform (HEVCe.c:515) + per-coefficient RDOQ (HEVCe.c:563-586); tentative levels replace
-// the coefficients in place, the clamped magnitudes are summed per (row, group column) for the zero-out test
+// the coefficients in place, the clamped magnitudes are summed per (row, group column) for the zero-out test.
+// RD cost without the saturation tests of HEVCe.c:182-184: here dist <= 2^24 and rate <= 1.1e6, so neither product
+// nor the sum can reach 2^31 and the plain weighted sum is the same number.
 template <int T>
 HEVCE_HD inline void phase_b_item(Shared& sm, const Grp& g, int item, int q, const RdK& rk) {
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, A2 = LG + 6;
     const int c = item >> LG, y = item & (T - 1);
     s16* bp = g.blk + c * BLK + y * T;
-    int v[T], o[T];
+    {
+        int v[T], o[T];
 #pragma unroll
-    for (int x = 0; x < T; x++) v[x] = bp[x];
-    Xf<T>::f(v, o);
+        for (int x = 0; x < T; x++) v[x] = bp[x];
+        Xf<T>::f(v, o);
+#pragma unroll
+        for (int x = 0; x < T; x++) bp[x] = (s16)((o[x] + (1 << A2 >> 1)) >> A2);
+    }
     const int dsh = 10 - LG, sh = 21 - LG + q, add = 1 << sh >> 1, thr = 9 << sh >> 2;
+    const int wd = rk.wd, wb = rk.wb;
     int* ps = g.psum + c * (T * T / 4) + y * (T / 4);
-#pragma unroll
+#pragma unroll 1
     for (int gx = 0; gx < T / 4; gx++) {
         int sum = 0;
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const int x = gx * 4 + e;
-            const int cf = (o[x] + (1 << A2 >> 1)) >> A2;
+            const int cf = bp[x];
             const int dl = iabs(cf) << 14;                       // |cf| <= 32640: the clamps of HEVCe.c:566 cannot trigger
             int lvl = (dl + add) >> sh;
             int pick = 0;
@@ -794,29 +808,28 @@ HEVCE_HD inline void phase_b_item(Shared& sm, const Grp& g, int item, int q, con
                 for (; lvl >= lo; lvl--) {
                     const int d1 = iabs(dl - (lvl << sh)) >> dsh;
                     const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
-                    int rate;                                    // HEVCe.c:526-535
-                    if (lvl < 6) rate = lvl == 0 ? 0 : lvl == 1 ? 70000 : lvl == 2 ? 90000 : lvl == 3 ? 92000 : lvl == 4 ? 157536 : 190304;
-                    else rate = 92000 + ((4 + 2 * (bitlen((unsigned)(lvl - 5)) - 1)) << 15);
-                    const int cost = rd_cost(rk, d, rate);
+                    const int wr = lvl < 6 ? sm.rate6[lvl] : wb * (92000 + ((4 + 2 * (bitlen((unsigned)(lvl - 5)) - 1)) << 15));   // HEVCe.c:526-535
+                    const int cost = wd * d + wr;
                     if (cost < best) { best = cost; pick = lvl; }
                 }
-            }
-            bp[x] = (s16)(cf < 0 ? -pick : pick);
+                bp[x] = (s16)(cf < 0 ? -pick : pick);
+            } else bp[x] = 0;
             sum += imin(dl, thr);
         }
         ps[gx] = sum;
     }
 }
 
-// phase C: group zero-out (HEVCe.c:589-592), final levels -> global store + non-zero-group bitmap, dequantisation
-// (HEVCe.c:600-615), inverse column transform (HEVCe.c:514 with inverse=1)
+// phase C: group zero-out (HEVCe.c:589-592), final levels -> global store (group-blocked, scan order) + non-zero-group
+// bitmap, dequantisation (HEVCe.c:600-615), inverse column transform (HEVCe.c:514 with inverse=1)
 template <int T>
 HEVCE_HD inline void phase_c_item(Shared& sm, const Scratch& sc, const Grp& g, int item, int q) {
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK;
     const int c = item >> LG, x = item & (T - 1), gx = x >> 2, ci = g.cand0 + c;
     s16* bp = g.blk + c * BLK + x;
     const int* ps = g.psum + c * (T * T / 4) + gx;
-    s16* lp = sc.glev + (size_t)ci * LEV_STRIDE + g.tu * (T * T) + x;
+    const u8* inv = sm.tb.inv4[scan_type(T, g.mode0 + c)] + (x & 3);
+    s16* lp = sc.glev + (size_t)ci * LEV_STRIDE + g.tu * (T * T) + gx * 16;
     const int sh = 21 - LG + q, thr = 9 << sh >> 2, qs = 7 - LG + q;
     int v[T], o[T];
     unsigned mlo = 0, mhi = 0;
@@ -830,7 +843,7 @@ HEVCE_HD inline void phase_c_item(Shared& sm, const Scratch& sc, const Grp& g, i
         for (int r = 0; r < 4; r++) {
             const int y = gy * 4 + r;
             const int l = keep ? (int)bp[y * T] : 0;
-            lp[y * T] = (s16)l;
+            lp[gy * (T / 4) * 16 + inv[r * 4]] = (s16)l;
             nzc |= l;
             v[y] = iclip(l * (1 << qs), -32768, 32767);
         }
@@ -868,6 +881,9 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
 #pragma unroll
         for (int x = 0; x < T; x++) v[x] = bp[x];
         Xf<T>::i(v, o);
+    } else {
+#pragma unroll
+        for (int x = 0; x < T; x++) o[x] = 0;
     }
     const int ry = g.ty - g.cuy + y, rx = g.tx - g.cux;
     u8* rs = g.rec ? g.rec + c * g.rec_stride + ry * g.rec_pitch + rx : nullptr;
@@ -875,7 +891,7 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
     int sse = 0;
 #pragma unroll
     for (int x = 0; x < T; x++) {
-        const int res = nzw ? iclip((o[x] + 2048) >> 12, -32768, 32767) : 0;
+        const int res = iclip((o[x] + 2048) >> 12, -32768, 32767);
         const int rec = iclip(res + pp[x], 0, 255);
         const int d = (int)org[x] - rec;
         sse += d * d;
@@ -885,11 +901,29 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
     HEVCE_ATOMIC_ADD(&sm.cand_sse[ci], sse);
 }
 
+// phase runners: one (non-inlined) copy per TU size, shared by all node sizes
 template <int T>
-HEVCE_HD inline void run_borders(Shared& sm, const Grp& g, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_borders(Shared& sm, const Grp& g, int off) {
     if (g.n == 0) return;
     const int n = (g.priv ? g.n : (T > 4 ? 2 : 1)) * (4 * T + 1);
     PAR_FOR_OFF(item, n, off) border_item<T>(sm, g, item);
+}
+template <int T>
+HEVCE_HD HEVCE_NOINLINE void run_phase_a(Shared& sm, const Grp& g, int off) {
+    PAR_FOR_OFF(item, g.n * T, off) phase_a_item<T>(sm, g, item);
+}
+template <int T>
+HEVCE_HD HEVCE_NOINLINE void run_phase_b(Shared& sm, const Grp& g, int off, int q) {
+    const RdK rk = rd_consts(q);
+    PAR_FOR_OFF(item, g.n * T, off) phase_b_item<T>(sm, g, item, q, rk);
+}
+template <int T>
+HEVCE_HD HEVCE_NOINLINE void run_phase_c(Shared& sm, const Scratch& sc, const Grp& g, int off, int q) {
+    PAR_FOR_OFF(item, g.n * T, off) phase_c_item<T>(sm, sc, g, item, q);
+}
+template <int T>
+HEVCE_HD HEVCE_NOINLINE void run_phase_d(Shared& sm, const Scratch& sc, const Grp& g, int off) {
+    PAR_FOR_OFF(item, g.n * T, off) phase_d_item<T>(sm, sc, g, item);
 }
 
 // shared-memory carve-up of the pool for a node of size S: group 0 = one-TU candidates (T = S), group 1 = four-TU
@@ -925,56 +959,47 @@ template <int S> struct Plan {
     static_assert(S != 8 || TOTAL <= AUX_CODER, "8x8 pipeline buffers overlap the trial-coder results");
 };
 
-template <bool E>
-HEVCE_HD inline Bac<E> make_bac(const Coder& c, const Tables* tb) {
-    Bac<E> b;
+HEVCE_HD inline Bac make_bac(const Coder& c, const Tables* tb) {
+    Bac b;
     b.c = c; b.out = nullptr; b.cap = 0; b.tb = tb;
     return b;
 }
 
-// trial entropy coding of one non-NxN candidate from the node snapshot (HEVCe.c:1434-1438, 1470-1474)
+// One trial-coder lane: candidates 0..69 code the whole CU from the node snapshot (HEVCe.c:1434-1438, 1470-1474);
+// candidates 70..104 are NxN PU modes: residual alone from a fresh coder and fresh contexts (HEVCe.c:1505-1519).
 template <int S>
-HEVCE_HD inline void trial_cabac(Shared& sm, const Scratch& sc, int cand, int depth, int gtL, int gtA, int pmL, int pmA) {
+HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int cand, int depth, int split_ctx, int pmL, int pmA) {
     constexpr int H = S / 2;
-    const int step = cand >= NMODE, mode = cand - step * NMODE;
-    Bac<false> b = make_bac<false>(sm.snap[depth], &sm.tb);
-    const CtxLane cx = {(u8*)sm.lane_ctx + 4 * cand};
+    const bool pu = cand >= 2 * NMODE;
+    const int step = cand / NMODE, mode = cand - step * NMODE;
+    Bac b = make_bac(sm.snap[depth], &sm.tb);
+    if (pu) coder_reset(b.c);
+    const int base_len = pu ? coder_len(b.c) : coder_len(sm.snap[depth]);
+    const Cx cx = {(u8*)(sm.lane_ctx + cand), 4 * NCAND};
     {
-        const u32* src = (const u32*)sm.snap_ctx[depth];
+        const u32* src = (const u32*)(pu ? sm.ctx0 : sm.snap_ctx[depth]);
         u32* dst = sm.lane_ctx + cand;
+#pragma unroll 4
         for (int k = 0; k < CTXW; k++) dst[k * NCAND] = src[k];
     }
-    const CgBuf cg = {cg_staging(sm) + cand};
-    put_split_cu(b, cx, S, 0, gtL, gtA);
+    CuDesc d;
+    d.s = S; d.kind = pu ? 3 : step; d.split_ctx = split_ctx;
+    d.pm[0] = mode; d.pl[0] = pmL; d.pa[0] = pmA;
     const s16* lev = sc.glev + (size_t)cand * LEV_STRIDE;
-    put_cu(b, cx, S, step, &mode, &pmL, &pmA, cg, [&](int k, LevSrc& src, unsigned& mlo, unsigned& mhi) {
-        if (step == 0) { src.p = lev; src.pitch = S; mlo = sm.cgnz[cand][0]; mhi = sm.cgnz[cand][1]; }
-        else { src.p = lev + k * H * H; src.pitch = H; mlo = sm.cgnz[cand][k]; mhi = 0; }
-    });
-    sm.cand_bits[cand] = coder_len(b.c) - coder_len(sm.snap[depth]);
-    cand_coder(sm)[cand] = b.c;
-}
-
-// NxN PU candidate: residual coding alone from a fresh coder and fresh contexts (HEVCe.c:1505-1519)
-HEVCE_HD inline void pu_cabac(Shared& sm, const Scratch& sc, int cand, int mode) {
-    Bac<false> b;
-    coder_reset(b.c);
-    b.out = nullptr; b.cap = 0; b.tb = &sm.tb;
-    const CtxLane cx = {(u8*)sm.lane_ctx + 4 * cand};
-    {
-        const u32* src = (const u32*)sm.ctx0;
-        u32* dst = sm.lane_ctx + cand;
-        for (int k = 0; k < CTXW; k++) dst[k * NCAND] = src[k];
+    if (step == 1) {
+        for (int k = 0; k < 4; k++) { d.lev[k] = lev + k * H * H; d.mlo[k] = sm.cgnz[cand][k]; }
+        d.mhi = 0;
+    } else {
+        d.lev[0] = lev; d.mlo[0] = sm.cgnz[cand][0]; d.mhi = pu ? 0u : sm.cgnz[cand][1];
     }
-    const CgBuf cg = {cg_staging(sm) + cand};
-    const LevSrc src = {sc.glev + (size_t)cand * LEV_STRIDE, 4};
-    put_residual(b, cx, 4, mode, src, sm.cgnz[cand][0], 0u, cg);
-    sm.cand_bits[cand] = coder_len(b.c);
+    code_cu(b, cx, d);
+    sm.cand_bits[cand] = coder_len(b.c) - base_len;
+    if (!pu) cand_coder(sm)[cand] = b.c;
 }
 
 // Evaluate the non-split candidates of one CU node and adopt the winner (HEVCe.c:1420-1559).
 template <int S>
-HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int x0, const Avail& av, int depth) {
+HEVCE_HD HEVCE_NOINLINE void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int x0, const Avail& av, int depth) {
     typedef Plan<S> P;
     constexpr int H = S / 2, N4 = S / 4, NSTEP = S == 8 ? 3 : 2;
     const RdK rk = rd_consts(q);
@@ -1020,36 +1045,35 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
             g2.blk = (s16*)(pool + P::BLK2); g2.pred = pool + P::PRED2; g2.psum = (int*)(pool + P::PSUM2); g2.bord = pool + P::BORD2;
             g2.rec = pool + P::REC2; g2.rec_stride = 16; g2.rec_pitch = 4;
         }
-        const int i0 = g0.n * S, i1 = g1.n * H, i2 = g2.n * 4;
+        const int i0 = g0.n * S, i1 = g1.n * H;
         // ---- phase 0: reference samples
         run_borders<S>(sm, g0, 0);
         run_borders<H>(sm, g1, 2 * (4 * S + 1));
         if (S == 8) run_borders<4>(sm, g2, 2 * (4 * S + 1) + g1.n * (4 * H + 1));
         PHASE_END();
         // ---- phase A
-        PAR_FOR_OFF(item, i0, 0) phase_a_item<S>(sm, g0, item);
-        PAR_FOR_OFF(item, i1, i0) phase_a_item<H>(sm, g1, item);
-        if (S == 8) { PAR_FOR_OFF(item, i2, i0 + i1) phase_a_item<4>(sm, g2, item); }
+        if (g0.n) run_phase_a<S>(sm, g0, 0);
+        run_phase_a<H>(sm, g1, i0);
+        if (S == 8) run_phase_a<4>(sm, g2, i0 + i1);
         PHASE_END();
         // ---- phase B
-        PAR_FOR_OFF(item, i0, 0) phase_b_item<S>(sm, g0, item, q, rk);
-        PAR_FOR_OFF(item, i1, i0) phase_b_item<H>(sm, g1, item, q, rk);
-        if (S == 8) { PAR_FOR_OFF(item, i2, i0 + i1) phase_b_item<4>(sm, g2, item, q, rk); }
+        if (g0.n) run_phase_b<S>(sm, g0, 0, q);
+        run_phase_b<H>(sm, g1, i0, q);
+        if (S == 8) run_phase_b<4>(sm, g2, i0 + i1, q);
         PHASE_END();
         // ---- phase C
-        PAR_FOR_OFF(item, i0, 0) phase_c_item<S>(sm, sc, g0, item, q);
-        PAR_FOR_OFF(item, i1, i0) phase_c_item<H>(sm, sc, g1, item, q);
-        if (S == 8) { PAR_FOR_OFF(item, i2, i0 + i1) phase_c_item<4>(sm, sc, g2, item, q); }
+        if (g0.n) run_phase_c<S>(sm, sc, g0, 0, q);
+        run_phase_c<H>(sm, sc, g1, i0, q);
+        if (S == 8) run_phase_c<4>(sm, sc, g2, i0 + i1, q);
         PHASE_END();
         // ---- phase D (+ the trial coders that only need the levels of phase C)
-        PAR_FOR_OFF(item, i0, 0) phase_d_item<S>(sm, sc, g0, item);
-        PAR_FOR_OFF(item, i1, i0) phase_d_item<H>(sm, sc, g1, item);
+        if (g0.n) run_phase_d<S>(sm, sc, g0, 0);
+        run_phase_d<H>(sm, sc, g1, i0);
         if (S == 8) {
-            PAR_FOR_OFF(item, i2, i0 + i1) phase_d_item<4>(sm, sc, g2, item);
+            run_phase_d<4>(sm, sc, g2, i0 + i1);
             PAR_FOR(t, NT) {
                 const int cand = lane_to_cand(NSTEP, t);
-                if (cand >= 2 * NMODE) pu_cabac(sm, sc, cand, cand - 2 * NMODE);
-                else if (cand >= 0 && r == 3) trial_cabac<S>(sm, sc, cand, depth, gtL, gtA, pmL, pmA);
+                if (cand >= 2 * NMODE || (cand >= 0 && r == 3)) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);
             }
         }
         PHASE_END();
@@ -1076,7 +1100,7 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
     if (S > 8) {   // all 70 trial coders of a 16x16 / 32x32 node
         PAR_FOR(t, NT) {
             const int cand = lane_to_cand(NSTEP, t);
-            if (cand >= 0) trial_cabac<S>(sm, sc, cand, depth, gtL, gtA, pmL, pmA);
+            if (cand >= 0) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);
         }
         PHASE_END();
     }
@@ -1084,23 +1108,20 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
     // ---- NxN as a whole + decision, reference order; every comparison is ">=" so the last minimum wins
     PAR_FOR(one, 1) {
         if (S == 8) {   // HEVCe.c:1531-1544
-            Bac<false> b = make_bac<false>(sm.snap[depth], &sm.tb);
-            const CtxFlat cx = {sm.nxn_ctx};
-            for (int i = 0; i < NCTX; i++) cx[i] = sm.snap_ctx[depth][i];
-            int pl[4], pa[4], pm[4];
-            for (int k = 0; k < 4; k++) pm[k] = sm.nxn_pm[k];
-            pl[0] = pmL;   pa[0] = pmA;
-            pl[1] = pm[0]; pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
-            pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; pa[2] = pm[0];
-            pl[3] = pm[2]; pa[3] = pm[1];
-            const CgBuf cg = {cg_staging(sm)};
-            put_split_cu(b, cx, S, 0, gtL, gtA);
-            put_cu(b, cx, S, 2, pm, pl, pa, cg, [&](int k, LevSrc& src, unsigned& mlo, unsigned& mhi) {
-                src.p = sm.nxn_lev[k]; src.pitch = 4; mlo = sm.nxn_nz[k]; mhi = 0;
-            });
+            Bac b = make_bac(sm.snap[depth], &sm.tb);
+            const Cx cx = {sm.nxn_ctx, 4};
+            for (int i = 0; i < CTXW; i++) ((u32*)sm.nxn_ctx)[i] = ((const u32*)sm.snap_ctx[depth])[i];
+            CuDesc d;
+            d.s = S; d.kind = 2; d.split_ctx = gtL + gtA; d.mhi = 0;
+            for (int k = 0; k < 4; k++) { d.pm[k] = sm.nxn_pm[k]; d.lev[k] = sm.nxn_lev[k]; d.mlo[k] = sm.nxn_nz[k]; }
+            d.pl[0] = pmL;     d.pa[0] = pmA;
+            d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
+            d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
+            d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
+            code_cu(b, cx, d);
             int sse = 0;
             for (int y = 0; y < 8; y++)
-                for (int x = 0; x < 8; x++) { const int d = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += d * d; }
+                for (int x = 0; x < 8; x++) { const int dd = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += dd * dd; }
             sm.nxn_cost = rd_cost(rk, sse, coder_len(b.c) - coder_len(sm.snap[depth]));
             sm.nxn_coder = b.c;
         }
@@ -1121,12 +1142,10 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
     const int win = sm.win_item;
     if (win < 0) return;   // the split stays: live state, window, levels and maps are already the children's
     // ---- adoption
+    s16* clev = sc.ctu_lev + zoff(y0, x0);
     if (win == NCAND) {
-        PAR_FOR(i, 64) {
-            const int k = i >> 4, j = i & 15, oy = (k >> 1) * 4, ox = (k & 1) * 4;
-            sc.ctu_lev[(y0 + oy + (j >> 2)) * CTU + x0 + ox + (j & 3)] = sm.nxn_lev[k][j];
-        }
-        PAR_FOR(i, NCTX) sm.live_ctx[i] = sm.nxn_ctx[i];
+        PAR_FOR(i, 64) clev[i] = sm.nxn_lev[i >> 4][i & 15];
+        PAR_FOR(i, CTXW) ((u32*)sm.live_ctx)[i] = ((const u32*)sm.nxn_ctx)[i];
         PAR_FOR(one, 1) {
             sm.live = sm.nxn_coder;
             sm.kind[(y0 >> 3) * 4 + (x0 >> 3)] = 2;
@@ -1140,15 +1159,10 @@ HEVCE_HD inline void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int
         const u8* rp = sc.grec + (size_t)win * (CTU * CTU);
         const s16* lp = sc.glev + (size_t)win * LEV_STRIDE;
         PAR_FOR(i, S * S) {
-            const int y = i / S, x = i % S;
-            HEVCE_WIN(sm, y0 + y, x0 + x) = rp[i];
-            int li;
-            if (step == 0) li = i;
-            else { const int k = (y >= H) * 2 + (x >= H); li = k * H * H + (y % H) * H + (x % H); }
-            sc.ctu_lev[(y0 + y) * CTU + x0 + x] = lp[li];
+            HEVCE_WIN(sm, y0 + i / S, x0 + i % S) = rp[i];
+            clev[i] = lp[i];
         }
-        const CtxLane cx = {(u8*)sm.lane_ctx + 4 * win};
-        PAR_FOR(i, NCTX) sm.live_ctx[i] = cx[i];
+        PAR_FOR(i, CTXW) ((u32*)sm.live_ctx)[i] = sm.lane_ctx[i * NCAND + win];
         PAR_FOR(i, N4 * N4) {
             const int idx = (my + i / N4) * 9 + mx + i % N4;
             sm.msz[idx] = (u8)S;
@@ -1172,9 +1186,9 @@ HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
     if (S > 8) {
         PAR_FOR(one, 1) {
             const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
-            Bac<false> b = make_bac<false>(sm.live, &sm.tb);
-            const CtxFlat cx = {sm.live_ctx};
-            put_split_cu(b, cx, S, 1, S > sm.msz[my * 9 + mx - 1], S > sm.msz[(my - 1) * 9 + mx]);
+            Bac b = make_bac(sm.live, &sm.tb);
+            const Cx cx = {sm.live_ctx, 4};
+            b.put_bin(1, cx[CX_SPLIT_CU + (S > sm.msz[my * 9 + mx - 1]) + (S > sm.msz[(my - 1) * 9 + mx])]);   // HEVCe.c:943-947
             sm.live = b.c;
         }
         PHASE_END();
@@ -1182,41 +1196,40 @@ HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
 }
 
 // re-encode the decided CTU with the byte-writing coder (replaces the reference's per-trial byte buffers)
-HEVCE_HD inline void commit_cu(Bac<true>& b, const CtxFlat& cx, const Shared& sm, const CgBuf& cg, const s16* lev, int s, int y0, int x0) {
+HEVCE_HD inline void commit_cu(Bac& b, const Cx& cx, const Shared& sm, const s16* ctu_lev, int s, int y0, int x0) {
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4, h = s / 2;
-    const int kind = sm.kind[(y0 >> 3) * 4 + (x0 >> 3)];
-    int pm[4], pl[4], pa[4];
-    pm[0] = sm.mpm[my * 9 + mx];
-    pl[0] = sm.mpm[my * 9 + mx - 1];
-    pa[0] = sm.mpm[(my - 1) * 9 + mx];
-    if (kind == 2) {
-        pm[1] = sm.mpm[my * 9 + mx + 1]; pm[2] = sm.mpm[(my + 1) * 9 + mx]; pm[3] = sm.mpm[(my + 1) * 9 + mx + 1];
-        pl[1] = pm[0]; pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
-        pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; pa[2] = pm[0];
-        pl[3] = pm[2]; pa[3] = pm[1];
+    CuDesc d;
+    d.s = s; d.kind = sm.kind[(y0 >> 3) * 4 + (x0 >> 3)]; d.split_ctx = -1; d.mhi = 0;
+    d.pm[0] = sm.mpm[my * 9 + mx];
+    d.pl[0] = sm.mpm[my * 9 + mx - 1];
+    d.pa[0] = sm.mpm[(my - 1) * 9 + mx];
+    if (d.kind == 2) {
+        d.pm[1] = sm.mpm[my * 9 + mx + 1]; d.pm[2] = sm.mpm[(my + 1) * 9 + mx]; d.pm[3] = sm.mpm[(my + 1) * 9 + mx + 1];
+        d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
+        d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
+        d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
     }
-    put_cu(b, cx, s, kind, pm, pl, pa, cg, [&](int k, LevSrc& src, unsigned& mlo, unsigned& mhi) {
-        const int oy = kind == 0 ? 0 : (k >> 1) * h, ox = kind == 0 ? 0 : (k & 1) * h;
-        src.p = lev + (y0 + oy) * CTU + x0 + ox;
-        src.pitch = CTU;
-        scan_groups(src, kind == 0 ? s : h, mlo, mhi);
-    });
+    const s16* lev = ctu_lev + zoff(y0, x0);
+    if (d.kind == 0) { d.lev[0] = lev; scan_groups(lev, s, d.mlo[0], d.mhi); }
+    else
+        for (int k = 0; k < 4; k++) { unsigned hi; d.lev[k] = lev + k * h * h; scan_groups(d.lev[k], h, d.mlo[k], hi); }
+    code_cu(b, cx, d);
 }
 
-HEVCE_HD inline void commit_ctu(Bac<true>& b, const CtxFlat& cx, const Shared& sm, const CgBuf& cg, const s16* lev) {
-    auto gt = [&](int s, int y, int x, int dy, int dx) { return s > sm.msz[(1 + y / 4 + dy) * 9 + 1 + x / 4 + dx]; };
-    if (sm.msz[10] == 32) {
-        put_split_cu(b, cx, 32, 0, gt(32, 0, 0, 0, -1), gt(32, 0, 0, -1, 0));
-        commit_cu(b, cx, sm, cg, lev, 32, 0, 0);
-        return;
-    }
-    put_split_cu(b, cx, 32, 1, gt(32, 0, 0, 0, -1), gt(32, 0, 0, -1, 0));
+HEVCE_HD inline void commit_ctu(Bac& b, const Cx& cx, const Shared& sm, const s16* lev) {
+    auto gt = [&](int s, int y, int x) { return (s > sm.msz[(1 + y / 4) * 9 + 1 + x / 4 - 1]) + (s > sm.msz[(1 + y / 4 - 1) * 9 + 1 + x / 4]); };
+    const int whole = sm.msz[10] == 32;
+    b.put_bin(!whole, cx[CX_SPLIT_CU + gt(32, 0, 0)]);
+    if (whole) { commit_cu(b, cx, sm, lev, 32, 0, 0); return; }
     for (int a = 0; a < 4; a++) {
         const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
         const int sz = sm.msz[(1 + y16 / 4) * 9 + 1 + x16 / 4];
-        put_split_cu(b, cx, 16, sz != 16, gt(16, y16, x16, 0, -1), gt(16, y16, x16, -1, 0));
-        if (sz == 16) { commit_cu(b, cx, sm, cg, lev, 16, y16, x16); continue; }
-        for (int c = 0; c < 4; c++) commit_cu(b, cx, sm, cg, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
+        b.put_bin(sz != 16, cx[CX_SPLIT_CU + gt(16, y16, x16)]);
+        const int ncu = sz == 16 ? 1 : 4;
+        for (int c = 0; c < ncu; c++) {
+            if (sz == 16) commit_cu(b, cx, sm, lev, 16, y16, x16);
+            else commit_cu(b, cx, sm, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
+        }
     }
 }
 
@@ -1262,7 +1275,7 @@ HEVCE_HD inline int write_header(u8* out, int q, int H, int W) {
 // ------------------------------------------------------------------------------------------------------------
 HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared& sm, const Scratch& sc) {
     const int q = job.q, H = job.H, W = job.W;
-    PAR_FOR(i, (int)sizeof(Tables)) ((u8*)&sm.tb)[i] = ((const u8*)&tables)[i];
+    PAR_FOR(i, (int)(sizeof(Tables) / 4)) ((u32*)&sm.tb)[i] = ((const u32*)&tables)[i];
     PHASE_END();
     PAR_FOR(i, 144) {
         const u8 v = i < NCTX ? ctx_init_value(sm.tb.ctx_iv[i], q) : (u8)0;
@@ -1271,6 +1284,10 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
     }
     PAR_FOR(i, 81) { sm.msz[i] = CTU; sm.mpm[i] = 1; }
     PAR_FOR(i, W / 4) sc.msz_line[i] = CTU;
+    PAR_FOR(lvl, 6) {
+        const RdK rk = rd_consts(q);
+        sm.rate6[lvl] = rk.wb * (lvl == 0 ? 0 : lvl == 1 ? 70000 : lvl == 2 ? 90000 : lvl == 3 ? 92000 : lvl == 4 ? 157536 : 190304);   // HEVCe.c:527
+    }
     PAR_FOR(one, 1) {
         coder_reset(sm.live);
         sm.error = 0;
@@ -1318,16 +1335,14 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
             PAR_FOR(i, 8) sc.msz_line[cx / 4 + i] = sm.msz[8 * 9 + 1 + i];
             PAR_FOR(one, 1) {
                 const int last = cy + CTU >= H && cx + CTU >= W;
-                Bac<false> t = make_bac<false>(sm.live, &sm.tb);
+                Bac t = make_bac(sm.live, &sm.tb);
                 t.put_terminate(last);                                                  // HEVCe.c:1630
                 if (last) t.finish();                                                   // HEVCe.c:1640
-                Bac<true> b;
-                b.c = sm.start; b.tb = &sm.tb;
+                Bac b = make_bac(sm.start, &sm.tb);
                 b.out = job.out + sm.stream_pos;
                 b.cap = imax(0, job.out_cap - sm.stream_pos);
-                const CtxFlat cxs = {sm.start_ctx};
-                const CgBuf cg = {cg_staging(sm)};
-                commit_ctu(b, cxs, sm, cg, sc.ctu_lev);
+                const Cx cxs = {sm.start_ctx, 4};
+                commit_ctu(b, cxs, sm, sc.ctu_lev);
                 b.put_terminate(last);
                 if (last) b.finish();
                 if (!coder_equal(b.c, t.c)) sm.error |= ERR_COMMIT_MISMATCH;
