@@ -43,7 +43,8 @@ typedef uint32_t u32;
 // sizes
 // ------------------------------------------------------------------------------------------------------------
 constexpr int CTU = 32;
-constexpr int NT = 128;            // threads per CTA
+constexpr int NT = 128;            // threads per picture
+constexpr int GANG = 4;            // pictures per CTA (lock-step groups of NT threads)
 constexpr int NCAND = 105;         // trial-coder lanes of a CU node: 35 one-TU + 35 four-TU + 35 NxN-PU candidates
 constexpr int NMODE = 35;
 constexpr int NCTX = 142;          // context bytes, same offsets as the reference struct (HEVCe.c:745-759)
@@ -590,8 +591,11 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 // work-item phases.  On the GPU a phase is a strided loop over the CTA's threads followed by __syncthreads();
 // in the simulator it is a loop over the items in a permuted order.
 #if defined(__CUDA_ARCH__)
-#define PAR_FOR(item, n) for (int item = (int)threadIdx.x; item < (n); item += NT)
-#define PAR_FOR_OFF(item, n, off) for (int item = (int)((threadIdx.x + NT - ((off) & (NT - 1))) & (NT - 1)); item < (n); item += NT)
+// A CTA holds GANG pictures of identical size, one per group of NT threads; the groups run the same phases in
+// lock-step (CTA-wide barriers), so every warp of the SM executes the same code at the same time.
+#define HEVCE_TID ((int)(threadIdx.x & (NT - 1)))
+#define PAR_FOR(item, n) for (int item = HEVCE_TID; item < (n); item += NT)
+#define PAR_FOR_OFF(item, n, off) for (int item = (HEVCE_TID + NT - ((off) & (NT - 1))) & (NT - 1); item < (n); item += NT)
 #define PHASE_END() __syncthreads()
 #define HEVCE_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define HEVCE_ATOMIC_ADD(p, v) atomicAdd((p), (v))
@@ -1139,11 +1143,12 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(Shared& sm, const Scratch& sc, int q, int
         sm.win_item = win;
     }
     PHASE_END();
-    const int win = sm.win_item;
-    if (win < 0) return;   // the split stays: live state, window, levels and maps are already the children's
+    const int win = sm.win_item;   // < 0: the split stays: live state, window, levels and maps are already the children's
     // ---- adoption
     s16* clev = sc.ctu_lev + zoff(y0, x0);
-    if (win == NCAND) {
+    if (win < 0) {
+        // nothing to adopt; still take the barrier below (all pictures of a CTA keep the same barrier sequence)
+    } else if (win == NCAND) {
         PAR_FOR(i, 64) clev[i] = sm.nxn_lev[i >> 4][i & 15];
         PAR_FOR(i, CTXW) ((u32*)sm.live_ctx)[i] = ((const u32*)sm.nxn_ctx)[i];
         PAR_FOR(one, 1) {

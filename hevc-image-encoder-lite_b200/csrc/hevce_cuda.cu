@@ -36,19 +36,22 @@ using namespace hevce;
 // ------------------------------------------------------------------------------------------------------------
 __device__ Tables g_tables;
 
-__global__ void __launch_bounds__(NT, 4)
-hevce_encode_kernel(const Job* __restrict__ jobs, const int* __restrict__ order, int njobs, const Scratch* __restrict__ slots, int* counter) {
+// A CTA = GANG pictures of identical padded size, one per group of NT threads.  `gangs` lists GANG job indices per
+// work unit (a short gang repeats its first job: the duplicate writes identical bytes).
+__global__ void __launch_bounds__(NT * GANG, 1)
+hevce_encode_kernel(const Job* __restrict__ jobs, const int* __restrict__ gangs, int ngangs, const Scratch* __restrict__ slots, int* counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Shared& sm = *reinterpret_cast<Shared*>(smem_raw);
+    const int member = threadIdx.x / NT;
+    Shared& sm = reinterpret_cast<Shared*>(smem_raw)[member];
     __shared__ int s_next;
-    const Scratch sc = slots[blockIdx.x];
+    const Scratch sc = slots[blockIdx.x * GANG + member];
     for (;;) {
         if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
         __syncthreads();
         const int k = s_next;
         __syncthreads();
-        if (k >= njobs) break;
-        const Job job = jobs[order[k]];
+        if (k >= ngangs) break;
+        const Job job = jobs[gangs[k * GANG + member]];
         encode_picture(job, g_tables, sm, sc);
     }
 }
@@ -99,8 +102,8 @@ int device_prepare(int device) {
     fill_tables(host_tables);
     CK(cudaMemcpyToSymbol(g_tables, &host_tables, sizeof(Tables)));
     int occ = 0;
-    CK(cudaFuncSetAttribute(hevce_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevce_encode_kernel, NT, sizeof(Shared)));
+    CK(cudaFuncSetAttribute(hevce_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GANG * sizeof(Shared))));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevce_encode_kernel, NT * GANG, GANG * sizeof(Shared)));
     if (occ < 1) occ = 1;
     g_dev[device].sms = prop.multiProcessorCount;
     g_dev[device].ctas_per_sm = occ;
@@ -123,7 +126,7 @@ int grow(T** p, size_t* cap, size_t need) {   // grow-only device buffer
 }   // namespace
 
 struct hevce_session {
-    int device = 0, n = 0, grid = 0, launches = 0;
+    int device = 0, n = 0, grid = 0, launches = 0, ngangs = 0;
     float kernel_ms = 0.f;
     long long h2d = 0, d2h = 0;
     cudaStream_t stream = nullptr;
@@ -184,16 +187,35 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     }
     s->img_total = io; s->rcon_total = ro; s->out_total = oo;
     if (n == 0) return 0;
+    // work units: gangs of GANG pictures with identical padded size, largest pictures first
+    s->order.resize(n);
+    std::iota(s->order.begin(), s->order.end(), 0);
+    std::stable_sort(s->order.begin(), s->order.end(), [&](int a, int b) {
+        const Job &x = s->jobs[a], &y = s->jobs[b];
+        const long long ax = (long long)x.H * x.W, ay = (long long)y.H * y.W;
+        if (ax != ay) return ax > ay;
+        if (x.H != y.H) return x.H > y.H;
+        return false;
+    });
+    std::vector<int> gangs;
+    for (int i = 0; i < n;) {
+        const Job& f = s->jobs[s->order[i]];
+        int m = 1;
+        while (m < GANG && i + m < n && s->jobs[s->order[i + m]].H == f.H && s->jobs[s->order[i + m]].W == f.W) m++;
+        for (int k = 0; k < GANG; k++) gangs.push_back(s->order[i + (k < m ? k : 0)]);
+        i += m;
+    }
+    s->ngangs = (int)gangs.size() / GANG;
     const DeviceInfo& di = g_dev[s->device];
-    s->grid = std::min(n, di.sms * di.ctas_per_sm);
+    s->grid = std::min(s->ngangs, di.sms * di.ctas_per_sm);
     if ((rc = grow(&s->d_img, &s->c_img, io))) return rc;
     if ((rc = grow(&s->d_rcon, &s->c_rcon, ro))) return rc;
     if ((rc = grow(&s->d_out, &s->c_out, oo))) return rc;
     if ((rc = grow(&s->d_jobs, &s->c_jobs, (size_t)n))) return rc;
-    if ((rc = grow(&s->d_order, &s->c_order, (size_t)n))) return rc;
+    if ((rc = grow(&s->d_order, &s->c_order, gangs.size()))) return rc;
     if ((rc = grow(&s->d_results, &s->c_results, (size_t)2 * n))) return rc;
     if (!s->d_counter) CK(cudaMalloc((void**)&s->d_counter, sizeof(int)));
-    const size_t g = (size_t)s->grid, nlev = (size_t)NCAND * LEV_STRIDE + 64, nrec = (size_t)NREC * CTU * CTU;
+    const size_t g = (size_t)s->grid * GANG, nlev = (size_t)NCAND * LEV_STRIDE + 64, nrec = (size_t)NREC * CTU * CTU;
     s->line_pitch = maxW / 4 + 32;
     if ((rc = grow(&s->d_glev, &s->c_glev, g * nlev))) return rc;
     if ((rc = grow(&s->d_grec, &s->c_grec, g * nrec))) return rc;
@@ -214,15 +236,9 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
         j.out = s->d_out + s->out_off[i];
         j.result = s->d_results + 2 * i;
     }
-    // queue order: most CTUs first, so the tail of the persistent grid is short
-    s->order.resize(n);
-    std::iota(s->order.begin(), s->order.end(), 0);
-    std::stable_sort(s->order.begin(), s->order.end(), [&](int a, int b) {
-        return (long long)s->jobs[a].H * s->jobs[a].W > (long long)s->jobs[b].H * s->jobs[b].W;
-    });
     CK(cudaMemcpyAsync(s->d_slots, slots.data(), g * sizeof(Scratch), cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->d_jobs, s->jobs.data(), (size_t)n * sizeof(Job), cudaMemcpyHostToDevice, s->stream));
-    CK(cudaMemcpyAsync(s->d_order, s->order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_order, gangs.data(), gangs.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -264,7 +280,7 @@ extern "C" int hevce_session_encode(hevce_session* s) {
     if (s->n == 0) return 0;
     CK(cudaMemsetAsync(s->d_counter, 0, sizeof(int), s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
-    hevce_encode_kernel<<<s->grid, NT, sizeof(Shared), s->stream>>>(s->d_jobs, s->d_order, s->n, s->d_slots, s->d_counter);
+    hevce_encode_kernel<<<s->grid, NT * GANG, GANG * sizeof(Shared), s->stream>>>(s->d_jobs, s->d_order, s->ngangs, s->d_slots, s->d_counter);
     CK(cudaGetLastError());
     CK(cudaEventRecord(s->ev1, s->stream));
     CK(cudaStreamSynchronize(s->stream));
