@@ -203,7 +203,6 @@ struct Bac {
     Coder c;
     u8* out;            // commit only: destination of this CTU's bytes (nullptr for trials)
     int cap;            // commit only: bytes available at out
-    const Tables* tb;
 
     HEVCE_HD void emit(int byte) {   // HEVCe.c:821-832
         const int b = byte & 0xff;
@@ -216,7 +215,8 @@ struct Bac {
         c.n++;
         c.z = b ? 0 : c.z + 1;
     }
-    HEVCE_HD HEVCE_NOINLINE void carry_slow() {   // HEVCe.c:861-878
+    HEVCE_HD void carry_out() {   // HEVCe.c:859-879
+        if (c.nbits >= 12) return;
         const int lead = c.low >> (24 - c.nbits);
         c.nbits += 8;
         c.low &= (int)(0xFFFFFFFFu >> c.nbits);
@@ -228,14 +228,13 @@ struct Bac {
             for (; c.nbytes > 1; c.nbytes--) emit((0xff + carry) & 0xff);
         } else { c.nbytes = 1; c.held = lead; }
     }
-    HEVCE_HD void carry_out() { if (c.nbits < 12) carry_slow(); }   // HEVCe.c:859-860
-    HEVCE_HD void put_bin(int bin, u8& cx) {   // HEVCe.c:914-933
+    HEVCE_HD void put_bin(const Tables& tb, int bin, u8& cx) {   // HEVCe.c:914-933
         const int v = cx;
-        const int lps = tb->lps[(v >> 1) * 4 + ((c.range >> 6) & 3)];
+        const int lps = tb.lps[(v >> 1) * 4 + ((c.range >> 6) & 3)];
         c.range -= lps;
         if ((bin != 0) != (v & 1)) {
             const int nb = lps < 8 ? 6 : 9 - bitlen((unsigned)lps);   // renorm table, HEVCe.c:715
-            cx = tb->next_lps[v];
+            cx = tb.next_lps[v];
             c.low = (int)((unsigned)(c.low + c.range) << nb);
             c.range = lps << nb;
             c.nbits -= nb;
@@ -272,8 +271,9 @@ struct Bac {
     }
 };
 
-// context set: byte k at p[(k>>2)*s4 + (k&3)].  s4 = 4: plain array; s4 = 4*NCAND: lane-private column of the
-// word-interleaved shared-memory array (every lane owns one bank).
+// context set: byte k at base[(k>>2)*s4 + (k&3)].  s4 = 4: plain array; s4 = 4*NCAND: lane-private column of the
+// word-interleaved shared-memory array (every lane owns one bank).  The base pointer is always derived from the
+// picture's shared-memory block inside the function that uses it, so the accesses stay LDS/STS.
 struct Cx {
     u8* p;
     int s4;
@@ -292,217 +292,6 @@ HEVCE_HD inline void mpm_list(int l, int a, int (&m)[3]) {   // HEVCe.c:958-977
 HEVCE_HD inline int scan_type(int s, int m) {   // HEVCe.c:1134-1150
     if (s <= 8) { if (iabs(m - 26) <= 4) return 1; if (iabs(m - 10) <= 4) return 2; }
     return 0;
-}
-
-// Levels of a TU are stored group by group (groups in raster order, gy*ncg+gx), the 16 levels of a group in the
-// scan order of the candidate's mode: a trial coder fetches one group with two 16-byte loads.
-HEVCE_HD inline void load_group(const s16* p, u32 (&w)[8]) {
-#if defined(__CUDA_ARCH__)
-    const uint4 a = ((const uint4*)p)[0], b = ((const uint4*)p)[1];
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-#else
-    for (int i = 0; i < 8; i++) w[i] = (u32)(unsigned short)p[2 * i] | ((u32)(unsigned short)p[2 * i + 1] << 16);
-#endif
-}
-
-// residual_coding() of one TU (HEVCe.c:1173-1269), restructured around coefficient groups: the caller supplies the
-// bitmap of non-zero 4x4 groups (bit gy*8+gx), so all-zero groups cost one bin and no memory traffic; a coded group
-// is reduced to three bit-fields in scan order (non-zero mask, signs, min(|level|,3) classes) that drive every
-// context-coded bin; only escape magnitudes are read back from the store.
-HEVCE_HD HEVCE_NOINLINE void put_residual(Bac& b, const Cx cx, int s, int m, const s16* lev, unsigned mlo, unsigned mhi) {
-    const Tables* tb = b.tb;
-    const int st = scan_type(s, m), lg = ilog2(s), ncg = s >> 2;
-    const int sigbase = CX_SIG + 9 + (s >= 16 ? 12 : 0) + ((s == 8 && st) ? 6 : 0);
-    auto cgpos = [&](int g, int& cy, int& cxg) {
-        if (lg == 2) { cy = 0; cxg = 0; }
-        else if (st == 1) { cy = g >> 1; cxg = g & 1; }
-        else if (st == 2) { cy = g & 1; cxg = g >> 1; }
-        else { const int v = tb->cgdiag[lg - 3][g]; cy = v >> 3; cxg = v & 7; }
-    };
-    auto bit = [&](int cy, int cxg) -> int { const int k = cy * 8 + cxg; return (int)(((k < 32) ? (mlo >> k) : (mhi >> (k - 32))) & 1u); };
-    int gl = 0;
-    for (int g = ncg * ncg - 1; g > 0; g--) {
-        int cy, cxg;
-        cgpos(g, cy, cxg);
-        if (bit(cy, cxg)) { gl = g; break; }
-    }
-    int c1 = 1;
-    for (int g = gl; g >= 0; g--) {
-        int cy, cxg;
-        cgpos(g, cy, cxg);
-        const int on = bit(cy, cxg), first_cg = g == 0;
-        const int rgt = cxg < ncg - 1 && bit(cy, cxg + 1), dwn = cy < ncg - 1 && bit(cy + 1, cxg);
-        const int pat = (dwn << 1) | rgt;
-        if (g != gl && !first_cg) b.put_bin(on, cx[CX_SIGCG + (pat != 0)]);
-        if (!on && !first_cg) continue;
-        // ---- bit-fields of the group, scan order
-        const s16* gp = lev + (cy * ncg + cxg) * 16;
-        unsigned nzm = 0, sgn = 0, cls = 0;
-        if (on) {
-            u32 w[8];
-            load_group(gp, w);
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const int v = (int)(s16)(w[k >> 1] >> (16 * (k & 1)));
-                const unsigned a = (unsigned)imin(iabs(v), 3);
-                nzm |= (unsigned)(v != 0) << k;
-                sgn |= (unsigned)(v < 0) << k;
-                cls |= a << (2 * k);
-            }
-        }
-        int kstart = 15;
-        if (g == gl) {
-            kstart = nzm ? bitlen(nzm) - 1 : 0;
-            const int p4 = tb->scan4[st][kstart];
-            // last_sig_coeff_xy (HEVCe.c:1046-1087)
-            const int y = cy * 4 + (p4 >> 2), x = cxg * 4 + (p4 & 3);
-            const int row = lg - 2, sh = s > 4;
-            int ty = st == 2 ? x : y, tx = st == 2 ? y : x;
-            const int gy = tb->grp[ty], gx = tb->grp[tx], gmax = tb->grp[s - 1];
-            const int bx = CX_LASTX + 5 * row, by = CX_LASTY + 5 * row;
-            for (int i = 0; i < gx; i++) b.put_bin(1, cx[bx + (i >> sh)]);
-            if (gx < gmax) b.put_bin(0, cx[bx + (gx >> sh)]);
-            for (int i = 0; i < gy; i++) b.put_bin(1, cx[by + (i >> sh)]);
-            if (gy < gmax) b.put_bin(0, cx[by + (gy >> sh)]);
-            if (gx > 3) { tx -= tb->gmin[gx]; for (int i = ((gx - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((tx >> i) & 1, 1); }   // one bin per call,
-            if (gy > 3) { ty -= tb->gmin[gy]; for (int i = ((gy - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((ty >> i) & 1, 1); }   // as HEVCe.c:1076-1086
-        }
-        // ---- sig_coeff_flags (HEVCe.c:1219-1222, context HEVCe.c:1092-1122)
-        {
-            const u32 soff = tb->sigoff[st][pat];
-            const unsigned long long s4 = tb->sig4[st];
-            const int base = sigbase + (first_cg ? 0 : 3);
-            int k = (g == gl) ? kstart - 1 : 15;
-            const int kend = (!first_cg && (nzm & ~1u) == 0) ? 1 : 0;   // position 0 of a later group is inferred when it is the only one
-            for (; k >= kend; k--) {
-                int ci;
-                if (s == 4) ci = CX_SIG + (int)((s4 >> (4 * k)) & 15u);
-                else if (first_cg && k == 0) ci = CX_SIG;
-                else ci = base + (int)((soff >> (2 * k)) & 3u);
-                b.put_bin((nzm >> k) & 1u, cx[ci]);
-            }
-        }
-        if (nzm) {
-            // ---- greater1 / greater2 flags, signs (HEVCe.c:1229-1252)
-            const int set = (first_cg ? 0 : 2) + (c1 == 0);
-            int nz = 0, signs = 0, g2 = -1;
-            c1 = 1;
-            unsigned mm = nzm;
-            while (mm) {
-                const int k = bitlen(mm) - 1;
-                mm &= ~(1u << k);
-                signs = (signs << 1) | (int)((sgn >> k) & 1u);
-                if (nz < 8) {
-                    const int a = (int)((cls >> (2 * k)) & 3u), big = a > 1;
-                    b.put_bin(big, cx[CX_ONE + 4 * set + c1]);
-                    if (big) { c1 = 0; if (g2 < 0) g2 = a > 2; else g2 |= 4; }
-                    else if (c1 > 0 && c1 < 3) c1++;
-                }
-                nz++;
-            }
-            int esc = nz > 8;
-            if (g2 >= 0) {
-                if (g2 & 4) esc = 1;
-                g2 &= 1;
-                if (c1 == 0) { b.put_bin(g2, cx[CX_ABS + set]); esc |= g2; }
-            }
-            b.put_bypass(signs, nz);
-            // ---- coeff_abs_level_remaining (HEVCe.c:1254-1266, 1154-1169)
-            if (esc) {
-                int base = 3, rp = 0, j = 0;
-                mm = nzm;
-                while (mm) {
-                    const int k = bitlen(mm) - 1;
-                    mm &= ~(1u << k);
-                    int a = (int)((cls >> (2 * k)) & 3u);
-                    if (a == 3) a = iabs((int)gp[k]);
-                    int v = a - (j < 8 ? base : 1);
-                    if (v >= 0) {
-                        if (v < (3 << rp)) {
-                            const int n = v >> rp;
-                            b.put_bypass((1 << (n + 1)) - 2, n + 1);
-                            b.put_bypass(v & ((1 << rp) - 1), rp);
-                        } else {
-                            int n = rp;
-                            v -= 3 << rp;
-                            for (; v >= (1 << n); n++) v -= 1 << n;
-                            const int pre = 4 + n - rp;
-                            b.put_bypass((1 << pre) - 2, pre);
-                            b.put_bypass(v, n);
-                        }
-                        if (a > (3 << rp)) rp = imin(rp + 1, 4);
-                    }
-                    if (a >= 2) base = 2;
-                    j++;
-                }
-            }
-        }
-    }
-}
-
-// One coding unit (HEVCe.c:1272-1340, 943-947).
-struct CuDesc {
-    int s;              // CU size
-    int kind;           // 0: 2Nx2N one TU, 1: 2Nx2N four TUs, 2: NxN, 3: residual of one TU only (NxN PU trial, HEVCe.c:1516)
-    int split_ctx;      // >= 0: code split_cu_flag = 0 with this context first (only s >= 16 codes it)
-    int pm[4], pl[4], pa[4];
-    const s16* lev[4];  // levels of TU k
-    unsigned mlo[4];    // non-zero-group bitmaps of TU k (low word); mhi: high word of TU 0 (32x32 only)
-    unsigned mhi;
-};
-
-HEVCE_HD HEVCE_NOINLINE void code_cu(Bac& b, const Cx cx, const CuDesc& d) {
-    const int s = d.s, kind = d.kind;
-    if (kind != 3) {
-        if (d.split_ctx >= 0 && s >= 16) b.put_bin(0, cx[CX_SPLIT_CU + d.split_ctx]);
-        if (s == 8) b.put_bin(kind != 2, cx[CX_PART]);
-        // luma modes (HEVCe.c:985-1018)
-        const int n = kind == 2 ? 4 : 1;
-        int hit[4], mp[4][3];
-        for (int i = 0; i < n; i++) {
-            mpm_list(d.pl[i], d.pa[i], mp[i]);
-            hit[i] = -1;
-            for (int j = 0; j < 3; j++) if (mp[i][j] == d.pm[i]) hit[i] = j;
-            b.put_bin(hit[i] >= 0, cx[CX_YPM]);
-        }
-        for (int i = 0; i < n; i++) {
-            if (hit[i] >= 0) {
-                b.put_bypass(hit[i] > 0, 1);
-                if (hit[i] > 0) b.put_bypass(hit[i] - 1, 1);
-            } else {
-                int r = d.pm[i];
-                const int hi = imax(mp[i][0], imax(mp[i][1], mp[i][2])), lo = imin(mp[i][0], imin(mp[i][1], mp[i][2]));
-                const int mid = mp[i][0] + mp[i][1] + mp[i][2] - hi - lo;
-                if (r > hi) r--;
-                if (r > mid) r--;
-                if (r > lo) r--;
-                b.put_bypass(r, 5);
-            }
-        }
-        b.put_bin(0, cx[CX_UVPM]);
-        if (kind != 2) b.put_bin(kind == 1, cx[CX_SPLIT_TU + (s == 32 ? 0 : s == 16 ? 1 : 2)]);
-        b.put_bin(0, cx[CX_UVCBF]);
-        b.put_bin(0, cx[CX_UVCBF]);
-    }
-    const int ntu = (kind == 0 || kind == 3) ? 1 : 4, ts = kind == 0 ? s : kind == 3 ? 4 : s >> 1;
-    for (int k = 0; k < ntu; k++) {
-        const unsigned mlo = d.mlo[k], mhi = k == 0 ? d.mhi : 0u;
-        const int on = (mlo | mhi) != 0;
-        if (kind != 3) b.put_bin(on, cx[CX_YCBF + (kind == 0)]);
-        if (on || kind == 3) put_residual(b, cx, ts, d.pm[kind == 2 ? k : 0], d.lev[k], mlo, mhi);
-    }
-}
-
-// bitmap of non-zero 4x4 groups of a stored TU (commit pass; the trial path gets it from phase C)
-HEVCE_HD inline void scan_groups(const s16* lev, int s, unsigned& mlo, unsigned& mhi) {
-    const int ncg = s >> 2;
-    mlo = mhi = 0;
-    for (int gy = 0; gy < ncg; gy++)
-        for (int gx = 0; gx < ncg; gx++) {
-            u32 w[8];
-            load_group(lev + (gy * ncg + gx) * 16, w);
-            if (w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) { const int k = gy * 8 + gx; if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
-        }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -545,6 +334,7 @@ struct Job {
 };
 
 enum { ERR_OVERFLOW = 1, ERR_COMMIT_MISMATCH = 2 };
+enum { P_BORDER, P_A, P_B, P_C, P_D_TRIAL, P_PU_ARGMIN, P_TRIAL, P_DECIDE, P_ADOPT, P_ENTER, P_LOAD, P_COMMIT, P_MISC, P_NTAGS };
 
 constexpr int LEV_STRIDE = CTU * CTU;   // per-candidate level store (all TUs of the candidate)
 constexpr int NREC = 70;                // candidates whose reconstruction is kept (one-TU + four-TU)
@@ -583,9 +373,20 @@ struct Shared {
     int win_item;                       // decision of the current node: -1 keep split, 0..NREC-1 candidate, NCAND = NxN
     int stream_pos;
     int error;
+    long long prof_last;
 };
 
 HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CODER); }
+
+// The picture's shared-memory block.  Non-inlined functions fetch it through this accessor instead of taking a
+// reference parameter: the compiler then knows the address space and emits LDS/STS instead of generic loads.
+#if defined(__CUDA_ARCH__)
+extern __shared__ __align__(16) unsigned char hevce_smem[];
+__device__ __forceinline__ Shared& my_sm() { return reinterpret_cast<Shared*>(hevce_smem)[threadIdx.x / NT]; }
+#else
+extern Shared* g_sim_sm;
+inline Shared& my_sm() { return *g_sim_sm; }
+#endif
 static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail too small");
 
 // work-item phases.  On the GPU a phase is a strided loop over the CTA's threads followed by __syncthreads();
@@ -597,6 +398,14 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 #define PAR_FOR(item, n) for (int item = HEVCE_TID; item < (n); item += NT)
 #define PAR_FOR_OFF(item, n, off) for (int item = (HEVCE_TID + NT - ((off) & (NT - 1))) & (NT - 1); item < (n); item += NT)
 #define PHASE_END() __syncthreads()
+#if defined(HEVCE_PROFILE)   // per-phase latency histogram (development builds only)
+extern __device__ unsigned long long g_phase_cycles[16];
+extern __device__ unsigned long long g_phase_count[16];
+#define PHASE_END_T(tag) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_ = clock64(); \
+    atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - sm.prof_last)); atomicAdd(&g_phase_count[tag], 1ull); sm.prof_last = t_; } } while (0)
+#else
+#define PHASE_END_T(tag) __syncthreads()
+#endif
 #define HEVCE_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define HEVCE_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #else
@@ -612,6 +421,7 @@ inline int sim_item(int i, int n) {
 #define PAR_FOR(item, n) for (int item##_i = 0, item = 0; item##_i < (n) && ((item = sim_item(item##_i, (n))), true); item##_i++)
 #define PAR_FOR_OFF(item, n, off) PAR_FOR(item, n)
 #define PHASE_END() ((void)0)
+#define PHASE_END_T(tag) ((void)0)
 #define HEVCE_ATOMIC_OR(p, v) (*(p) |= (v))
 #define HEVCE_ATOMIC_ADD(p, v) (*(p) += (v))
 #endif
@@ -635,6 +445,253 @@ HEVCE_HD inline int zoff(int y, int x) {
     return (((a & 2) << 2) | ((c & 2) << 1) | ((a & 1) << 1) | (c & 1)) * 64;
 }
 
+// Levels of a TU are stored group by group (groups in raster order, gy*ncg+gx), the 16 levels of a group in the
+// scan order of the candidate's mode: a trial coder fetches one group with two 16-byte loads.
+HEVCE_HD inline void load_group(const s16* p, u32 (&w)[8]) {
+#if defined(__CUDA_ARCH__)
+    const uint4 a = ((const uint4*)p)[0], b = ((const uint4*)p)[1];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) w[i] = (u32)(unsigned short)p[2 * i] | ((u32)(unsigned short)p[2 * i + 1] << 16);
+#endif
+}
+
+// one coefficient group: bit-fields in scan order, last position (first coded group only), sig flags, greater1/2,
+// signs, remaining levels.  w: the 16 levels (8 words), gp: the same group in the store (escape magnitudes).
+HEVCE_HD inline void code_group(Bac& b, const Tables& tbl, const Cx cx, int s, int st, int lg, int sigbase, const s16* gp, const u32 (&w)[8],
+                                int on, int pat, int first_cg, bool is_last, int cy, int cxg, int& c1) {
+    const Tables* tb = &tbl;
+    // ---- bit-fields of the group, scan order
+    unsigned nzm = 0, sgn = 0, cls = 0;
+    if (on) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int v = (int)(s16)(w[k >> 1] >> (16 * (k & 1)));
+            const unsigned a = (unsigned)imin(iabs(v), 3);
+            nzm |= (unsigned)(v != 0) << k;
+            sgn |= (unsigned)(v < 0) << k;
+            cls |= a << (2 * k);
+        }
+    }
+    int kstart = 15;
+    if (is_last) {
+        kstart = nzm ? bitlen(nzm) - 1 : 0;
+        const int p4 = tb->scan4[st][kstart];
+        // last_sig_coeff_xy (HEVCe.c:1046-1087)
+        const int y = cy * 4 + (p4 >> 2), x = cxg * 4 + (p4 & 3);
+        const int row = lg - 2, sh = s > 4;
+        int ty = st == 2 ? x : y, tx = st == 2 ? y : x;
+        const int gy = tb->grp[ty], gx = tb->grp[tx], gmax = tb->grp[s - 1];
+        const int bx = CX_LASTX + 5 * row, by = CX_LASTY + 5 * row;
+        for (int i = 0; i < gx; i++) b.put_bin(tbl, 1, cx[bx + (i >> sh)]);
+        if (gx < gmax) b.put_bin(tbl, 0, cx[bx + (gx >> sh)]);
+        for (int i = 0; i < gy; i++) b.put_bin(tbl, 1, cx[by + (i >> sh)]);
+        if (gy < gmax) b.put_bin(tbl, 0, cx[by + (gy >> sh)]);
+        if (gx > 3) { tx -= tb->gmin[gx]; for (int i = ((gx - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((tx >> i) & 1, 1); }   // one bin per call,
+        if (gy > 3) { ty -= tb->gmin[gy]; for (int i = ((gy - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((ty >> i) & 1, 1); }   // as HEVCe.c:1076-1086
+    }
+    // ---- sig_coeff_flags (HEVCe.c:1219-1222, context HEVCe.c:1092-1122)
+    {
+        const u32 soff = tb->sigoff[st][pat];
+        const unsigned long long s4 = tb->sig4[st];
+        const int base = sigbase + (first_cg ? 0 : 3);
+        int k = is_last ? kstart - 1 : 15;
+        const int kend = (!first_cg && (nzm & ~1u) == 0) ? 1 : 0;   // position 0 of a later group is inferred when it is the only one
+        for (; k >= kend; k--) {
+            int ci;
+            if (s == 4) ci = CX_SIG + (int)((s4 >> (4 * k)) & 15u);
+            else if (first_cg && k == 0) ci = CX_SIG;
+            else ci = base + (int)((soff >> (2 * k)) & 3u);
+            b.put_bin(tbl, (nzm >> k) & 1u, cx[ci]);
+        }
+    }
+    if (nzm) {
+        // ---- greater1 / greater2 flags, signs (HEVCe.c:1229-1252)
+        const int set = (first_cg ? 0 : 2) + (c1 == 0);
+        int nz = 0, signs = 0, g2 = -1;
+        c1 = 1;
+        unsigned mm = nzm;
+        while (mm) {
+            const int k = bitlen(mm) - 1;
+            mm &= ~(1u << k);
+            signs = (signs << 1) | (int)((sgn >> k) & 1u);
+            if (nz < 8) {
+                const int a = (int)((cls >> (2 * k)) & 3u), big = a > 1;
+                b.put_bin(tbl, big, cx[CX_ONE + 4 * set + c1]);
+                if (big) { c1 = 0; if (g2 < 0) g2 = a > 2; else g2 |= 4; }
+                else if (c1 > 0 && c1 < 3) c1++;
+            }
+            nz++;
+        }
+        int esc = nz > 8;
+        if (g2 >= 0) {
+            if (g2 & 4) esc = 1;
+            g2 &= 1;
+            if (c1 == 0) { b.put_bin(tbl, g2, cx[CX_ABS + set]); esc |= g2; }
+        }
+        b.put_bypass(signs, nz);
+        // ---- coeff_abs_level_remaining (HEVCe.c:1254-1266, 1154-1169)
+        if (esc) {
+            int base = 3, rp = 0, j = 0;
+            mm = nzm;
+            while (mm) {
+                const int k = bitlen(mm) - 1;
+                mm &= ~(1u << k);
+                int a = (int)((cls >> (2 * k)) & 3u);
+                if (a == 3) a = iabs((int)gp[k]);
+                int v = a - (j < 8 ? base : 1);
+                if (v >= 0) {
+                    if (v < (3 << rp)) {
+                        const int n = v >> rp;
+                        b.put_bypass((1 << (n + 1)) - 2, n + 1);
+                        b.put_bypass(v & ((1 << rp) - 1), rp);
+                    } else {
+                        int n = rp;
+                        v -= 3 << rp;
+                        for (; v >= (1 << n); n++) v -= 1 << n;
+                        const int pre = 4 + n - rp;
+                        b.put_bypass((1 << pre) - 2, pre);
+                        b.put_bypass(v, n);
+                    }
+                    if (a > (3 << rp)) rp = imin(rp + 1, 4);
+                }
+                if (a >= 2) base = 2;
+                j++;
+            }
+        }
+    }
+
+}
+
+// residual_coding() of one TU (HEVCe.c:1173-1269), restructured around coefficient groups: the caller supplies the
+// bitmap of non-zero 4x4 groups (bit gy*8+gx), so all-zero groups cost one bin and no memory traffic; a coded group
+// is reduced to three bit-fields in scan order (non-zero mask, signs, min(|level|,3) classes) that drive every
+// context-coded bin; only escape magnitudes are read back from the store.
+HEVCE_HD inline void put_residual(Bac& b, const Tables& tbl, const Cx cx, int s, int m, const s16* lev, unsigned mlo, unsigned mhi) {
+    const Tables* tb = &tbl;
+    const int st = scan_type(s, m), lg = ilog2(s), ncg = s >> 2;
+    const int sigbase = CX_SIG + 9 + (s >= 16 ? 12 : 0) + ((s == 8 && st) ? 6 : 0);
+    auto cgpos = [&](int g, int& cy, int& cxg) {
+        if (lg == 2) { cy = 0; cxg = 0; }
+        else if (st == 1) { cy = g >> 1; cxg = g & 1; }
+        else if (st == 2) { cy = g & 1; cxg = g >> 1; }
+        else { const int v = tb->cgdiag[lg - 3][g]; cy = v >> 3; cxg = v & 7; }
+    };
+    auto bit = [&](int cy, int cxg) -> int { const int k = cy * 8 + cxg; return (int)(((k < 32) ? (mlo >> k) : (mhi >> (k - 32))) & 1u); };
+    int gl = 0;
+    for (int g = ncg * ncg - 1; g > 0; g--) {
+        int cy, cxg;
+        cgpos(g, cy, cxg);
+        if (bit(cy, cxg)) { gl = g; break; }
+    }
+    int c1 = 1;
+    // groups are visited in reverse scan order; the levels of the next coded group are fetched while the current
+    // one is being coded (the store is L2-resident, a fetch costs several hundred cycles)
+    u32 w[8], wn[8];
+    int cy, cxg, ncy = 0, ncx = 0;
+    cgpos(gl, cy, cxg);
+    int on = bit(cy, cxg);
+    if (on) load_group(lev + (cy * ncg + cxg) * 16, w);
+    for (int g = gl;;) {
+        // next group that needs its levels: the next non-zero one, or the first group
+        int g2 = g - 1, on2 = 0;
+        for (; g2 > 0; g2--) {
+            cgpos(g2, ncy, ncx);
+            if (bit(ncy, ncx)) { on2 = 1; break; }
+        }
+        if (g2 == 0) { ncy = 0; ncx = 0; on2 = g > 0 ? bit(0, 0) : 0; }
+        if (on2) load_group(lev + (ncy * ncg + ncx) * 16, wn);
+        const int first_cg = g == 0;
+        {
+            const int rgt = cxg < ncg - 1 && bit(cy, cxg + 1), dwn = cy < ncg - 1 && bit(cy + 1, cxg);
+            const int pat = (dwn << 1) | rgt;
+            if (g != gl && !first_cg) b.put_bin(tbl, on, cx[CX_SIGCG + (pat != 0)]);
+            code_group(b, tbl, cx, s, st, lg, sigbase, lev + (cy * ncg + cxg) * 16, w, on, pat, first_cg, g == gl, cy, cxg, c1);
+        }
+        if (g == 0) break;
+        for (int gg = g - 1; gg > g2; gg--) {   // all-zero groups in between: coded_sub_block_flag = 0
+            int zy, zx;
+            cgpos(gg, zy, zx);
+            const int rgt = zx < ncg - 1 && bit(zy, zx + 1), dwn = zy < ncg - 1 && bit(zy + 1, zx);
+            b.put_bin(tbl, 0, cx[CX_SIGCG + ((rgt | dwn) != 0)]);
+        }
+        g = g2; cy = ncy; cxg = ncx; on = on2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = wn[i];
+    }
+}
+
+// One coding unit (HEVCe.c:1272-1340, 943-947).
+struct CuDesc {
+    int s;              // CU size
+    int kind;           // 0: 2Nx2N one TU, 1: 2Nx2N four TUs, 2: NxN, 3: residual of one TU only (NxN PU trial, HEVCe.c:1516)
+    int split_ctx;      // >= 0: code split_cu_flag = 0 with this context first (only s >= 16 codes it)
+    int pm[4], pl[4], pa[4];
+    const s16* lev[4];  // levels of TU k
+    unsigned mlo[4];    // non-zero-group bitmaps of TU k (low word); mhi: high word of TU 0 (32x32 only)
+    unsigned mhi;
+};
+
+HEVCE_HD HEVCE_NOINLINE void code_cu(Bac& bio, int cx_off, int cx_s4, const CuDesc& d) {
+    Shared& sm = my_sm();
+    const Tables& tbl = sm.tb;
+    const Cx cx = {(u8*)&sm + cx_off, cx_s4};
+    Bac b = bio;   // coder state in registers for the whole CU
+    const int s = d.s, kind = d.kind;
+    if (kind != 3) {
+        if (d.split_ctx >= 0 && s >= 16) b.put_bin(tbl, 0, cx[CX_SPLIT_CU + d.split_ctx]);
+        if (s == 8) b.put_bin(tbl, kind != 2, cx[CX_PART]);
+        // luma modes (HEVCe.c:985-1018)
+        const int n = kind == 2 ? 4 : 1;
+        int hit[4], mp[4][3];
+        for (int i = 0; i < n; i++) {
+            mpm_list(d.pl[i], d.pa[i], mp[i]);
+            hit[i] = -1;
+            for (int j = 0; j < 3; j++) if (mp[i][j] == d.pm[i]) hit[i] = j;
+            b.put_bin(tbl, hit[i] >= 0, cx[CX_YPM]);
+        }
+        for (int i = 0; i < n; i++) {
+            if (hit[i] >= 0) {
+                b.put_bypass(hit[i] > 0, 1);
+                if (hit[i] > 0) b.put_bypass(hit[i] - 1, 1);
+            } else {
+                int r = d.pm[i];
+                const int hi = imax(mp[i][0], imax(mp[i][1], mp[i][2])), lo = imin(mp[i][0], imin(mp[i][1], mp[i][2]));
+                const int mid = mp[i][0] + mp[i][1] + mp[i][2] - hi - lo;
+                if (r > hi) r--;
+                if (r > mid) r--;
+                if (r > lo) r--;
+                b.put_bypass(r, 5);
+            }
+        }
+        b.put_bin(tbl, 0, cx[CX_UVPM]);
+        if (kind != 2) b.put_bin(tbl, kind == 1, cx[CX_SPLIT_TU + (s == 32 ? 0 : s == 16 ? 1 : 2)]);
+        b.put_bin(tbl, 0, cx[CX_UVCBF]);
+        b.put_bin(tbl, 0, cx[CX_UVCBF]);
+    }
+    const int ntu = (kind == 0 || kind == 3) ? 1 : 4, ts = kind == 0 ? s : kind == 3 ? 4 : s >> 1;
+    for (int k = 0; k < ntu; k++) {
+        const unsigned mlo = d.mlo[k], mhi = k == 0 ? d.mhi : 0u;
+        const int on = (mlo | mhi) != 0;
+        if (kind != 3) b.put_bin(tbl, on, cx[CX_YCBF + (kind == 0)]);
+        if (on || kind == 3) put_residual(b, tbl, cx, ts, d.pm[kind == 2 ? k : 0], d.lev[k], mlo, mhi);
+    }
+    bio = b;
+}
+
+// bitmap of non-zero 4x4 groups of a stored TU (commit pass; the trial path gets it from phase C)
+HEVCE_HD inline void scan_groups(const s16* lev, int s, unsigned& mlo, unsigned& mhi) {
+    const int ncg = s >> 2;
+    mlo = mhi = 0;
+    for (int gy = 0; gy < ncg; gy++)
+        for (int gx = 0; gx < ncg; gx++) {
+            u32 w[8];
+            load_group(lev + (gy * ncg + gx) * 16, w);
+            if (w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) { const int k = gy * 8 + gx; if (k < 32) mlo |= 1u << k; else mhi |= 1u << (k - 32); }
+        }
+}
+
+
 // trial lanes: thread -> candidate.  Modes 0..31 of a step share a warp, the 3 leftover modes are packed behind.
 HEVCE_HD inline int lane_to_cand(int nsteps, int t) {   // returns step*35+mode, or -1
     if (t < nsteps * 32) return (t >> 5) * NMODE + (t & 31);
@@ -657,11 +714,12 @@ struct Grp {
     int tu;             // TU index inside the candidate (levels at tu*T*T, bitmap word)
     int one_tu;         // 1: one-TU candidate (bitmap uses words 0/1)
     int grec;           // 1: reconstruction rows also go to the global store (cand0 < NREC)
-    s16* blk;           // [n][T*T+T]   residual -> coefficients -> tentative levels -> inverse intermediate
-    u8* pred;           // [n][T*T]
-    int* psum;          // [n][T*T/4]   per (row, group column) sums for the group zero-out
-    u8* bord;           // shared: [2][4T+4] (unfiltered, filtered); private: [n][4T+4]
-    u8* rec;            // [n][rec_stride] candidate-private reconstruction, pitch rec_pitch, or nullptr
+    // byte offsets into Shared::pool (offsets, not pointers, so the accesses stay in the shared address space)
+    int blk;            // s16 [n][T*T+T]   residual -> coefficients -> tentative levels -> inverse intermediate
+    int pred;           // u8  [n][T*T]
+    int psum;           // int [n][T*T/4]   per (row, group column) sums for the group zero-out
+    int bord;           // u8  shared: [2][4T+4] (unfiltered, filtered); private: [n][4T+4]
+    int rec;            // u8  [n][rec_stride] candidate-private reconstruction, pitch rec_pitch; -1: none
     int rec_stride, rec_pitch;
 };
 
@@ -683,7 +741,7 @@ HEVCE_HD inline void border_item(Shared& sm, const Grp& g, int item) {
         const int yy = g.ty + y, xx = g.tx + x;
         if (g.priv) {
             const int cy = yy - g.cuy, cx = xx - g.cux;
-            if (cy >= 0 && cx >= 0 && cy < g.cus && cx < g.cus) return g.rec[cand * g.rec_stride + cy * g.rec_pitch + cx];
+            if (cy >= 0 && cx >= 0 && cy < g.cus && cx < g.cus) return sm.pool[g.rec + cand * g.rec_stride + cy * g.rec_pitch + cx];
         }
         return HEVCE_WIN(sm, yy, xx);
     };
@@ -707,7 +765,7 @@ HEVCE_HD inline void border_item(Shared& sm, const Grp& g, int item) {
     int v = u(j);
     const bool filt = g.priv ? use_filtered(T, g.mode0 + cand) != 0 : which == 1;
     if (T > 4 && filt && j > 0 && j < 4 * T) v = (2 + 2 * v + u(j - 1) + u(j + 1)) >> 2;
-    g.bord[which * BS + 1 + j] = (u8)v;
+    sm.pool[g.bord + which * BS + 1 + j] = (u8)v;
 }
 
 // phase A: prediction of column x (HEVCe.c:262-381), residual, forward column transform (HEVCe.c:514)
@@ -716,9 +774,9 @@ HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, BS = Dim<T>::BS, UNR = Dim<T>::UNR;
     const int c = item >> LG, x = item & (T - 1), m = g.mode0 + c;
     const int bsel = g.priv ? c : (T > 4 && use_filtered(T, m));
-    const u8* B = g.bord + bsel * BS + 1 + 2 * T;   // B[k]: k > 0 top[k-1], k < 0 left[-k-1], 0 corner
+    const u8* B = sm.pool + g.bord + bsel * BS + 1 + 2 * T;   // B[k]: k > 0 top[k-1], k < 0 left[-k-1], 0 corner
     const u8* org = sm.orig + g.ty * CTU + g.tx + x;
-    u8* pp = g.pred + c * (T * T) + x;
+    u8* pp = sm.pool + g.pred + c * (T * T) + x;
     if (x == 0) {   // per-candidate accumulators of this TU
         const int ci = g.cand0 + c;
         if (g.one_tu) { sm.cgnz[ci][0] = 0; sm.cgnz[ci][1] = 0; sm.cand_sse[ci] = 0; }
@@ -770,7 +828,7 @@ HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
 #pragma unroll
     for (int y = 0; y < T; y++) v[y] = (int)org[y * CTU] - (int)pp[y * T];
     Xf<T>::f(v, o);
-    s16* bp = g.blk + c * BLK + x;
+    s16* bp = (s16*)(sm.pool + g.blk) + c * BLK + x;
     constexpr int A1 = LG - 1;
 #pragma unroll
     for (int k = 0; k < T; k++) bp[k * T] = (s16)((o[k] + (1 << A1 >> 1)) >> A1);
@@ -784,7 +842,7 @@ template <int T>
 HEVCE_HD inline void phase_b_item(Shared& sm, const Grp& g, int item, int q, const RdK& rk) {
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, A2 = LG + 6;
     const int c = item >> LG, y = item & (T - 1);
-    s16* bp = g.blk + c * BLK + y * T;
+    s16* bp = (s16*)(sm.pool + g.blk) + c * BLK + y * T;
     {
         int v[T], o[T];
 #pragma unroll
@@ -795,7 +853,7 @@ HEVCE_HD inline void phase_b_item(Shared& sm, const Grp& g, int item, int q, con
     }
     const int dsh = 10 - LG, sh = 21 - LG + q, add = 1 << sh >> 1, thr = 9 << sh >> 2;
     const int wd = rk.wd, wb = rk.wb;
-    int* ps = g.psum + c * (T * T / 4) + y * (T / 4);
+    int* ps = (int*)(sm.pool + g.psum) + c * (T * T / 4) + y * (T / 4);
 #pragma unroll 1
     for (int gx = 0; gx < T / 4; gx++) {
         int sum = 0;
@@ -830,8 +888,8 @@ template <int T>
 HEVCE_HD inline void phase_c_item(Shared& sm, const Scratch& sc, const Grp& g, int item, int q) {
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK;
     const int c = item >> LG, x = item & (T - 1), gx = x >> 2, ci = g.cand0 + c;
-    s16* bp = g.blk + c * BLK + x;
-    const int* ps = g.psum + c * (T * T / 4) + gx;
+    s16* bp = (s16*)(sm.pool + g.blk) + c * BLK + x;
+    const int* ps = (const int*)(sm.pool + g.psum) + c * (T * T / 4) + gx;
     const u8* inv = sm.tb.inv4[scan_type(T, g.mode0 + c)] + (x & 3);
     s16* lp = sc.glev + (size_t)ci * LEV_STRIDE + g.tu * (T * T) + gx * 16;
     const int sh = 21 - LG + q, thr = 9 << sh >> 2, qs = 7 - LG + q;
@@ -877,8 +935,8 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK;
     const int c = item >> LG, y = item & (T - 1), ci = g.cand0 + c;
     const unsigned nzw = g.one_tu ? (sm.cgnz[ci][0] | sm.cgnz[ci][1]) : sm.cgnz[ci][g.tu];
-    const s16* bp = g.blk + c * BLK + y * T;
-    const u8* pp = g.pred + c * (T * T) + y * T;
+    const s16* bp = (const s16*)(sm.pool + g.blk) + c * BLK + y * T;
+    const u8* pp = sm.pool + g.pred + c * (T * T) + y * T;
     const u8* org = sm.orig + (g.ty + y) * CTU + g.tx;
     int v[T], o[T];
     if (nzw) {
@@ -890,7 +948,7 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
         for (int x = 0; x < T; x++) o[x] = 0;
     }
     const int ry = g.ty - g.cuy + y, rx = g.tx - g.cux;
-    u8* rs = g.rec ? g.rec + c * g.rec_stride + ry * g.rec_pitch + rx : nullptr;
+    u8* rs = g.rec >= 0 ? sm.pool + g.rec + c * g.rec_stride + ry * g.rec_pitch + rx : nullptr;
     u8* rg = g.grec ? sc.grec + (size_t)ci * (CTU * CTU) + ry * g.cus + rx : nullptr;
     int sse = 0;
 #pragma unroll
@@ -907,26 +965,31 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
 
 // phase runners: one (non-inlined) copy per TU size, shared by all node sizes
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_borders(Shared& sm, const Grp& g, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_borders(const Grp& g, int off) {
+    Shared& sm = my_sm();
     if (g.n == 0) return;
     const int n = (g.priv ? g.n : (T > 4 ? 2 : 1)) * (4 * T + 1);
     PAR_FOR_OFF(item, n, off) border_item<T>(sm, g, item);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_a(Shared& sm, const Grp& g, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_a(const Grp& g, int off) {
+    Shared& sm = my_sm();
     PAR_FOR_OFF(item, g.n * T, off) phase_a_item<T>(sm, g, item);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_b(Shared& sm, const Grp& g, int off, int q) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_b(const Grp& g, int off, int q) {
+    Shared& sm = my_sm();
     const RdK rk = rd_consts(q);
     PAR_FOR_OFF(item, g.n * T, off) phase_b_item<T>(sm, g, item, q, rk);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_c(Shared& sm, const Scratch& sc, const Grp& g, int off, int q) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_c(const Scratch& sc, const Grp& g, int off, int q) {
+    Shared& sm = my_sm();
     PAR_FOR_OFF(item, g.n * T, off) phase_c_item<T>(sm, sc, g, item, q);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_d(Shared& sm, const Scratch& sc, const Grp& g, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& sc, const Grp& g, int off) {
+    Shared& sm = my_sm();
     PAR_FOR_OFF(item, g.n * T, off) phase_d_item<T>(sm, sc, g, item);
 }
 
@@ -963,11 +1026,12 @@ template <int S> struct Plan {
     static_assert(S != 8 || TOTAL <= AUX_CODER, "8x8 pipeline buffers overlap the trial-coder results");
 };
 
-HEVCE_HD inline Bac make_bac(const Coder& c, const Tables* tb) {
+HEVCE_HD inline Bac make_bac(const Coder& c) {
     Bac b;
-    b.c = c; b.out = nullptr; b.cap = 0; b.tb = tb;
+    b.c = c; b.out = nullptr; b.cap = 0;
     return b;
 }
+HEVCE_HD inline int sm_off(const Shared& sm, const void* p) { return (int)((const u8*)p - (const u8*)&sm); }
 
 // One trial-coder lane: candidates 0..69 code the whole CU from the node snapshot (HEVCe.c:1434-1438, 1470-1474);
 // candidates 70..104 are NxN PU modes: residual alone from a fresh coder and fresh contexts (HEVCe.c:1505-1519).
@@ -976,10 +1040,9 @@ HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int cand, int dep
     constexpr int H = S / 2;
     const bool pu = cand >= 2 * NMODE;
     const int step = cand / NMODE, mode = cand - step * NMODE;
-    Bac b = make_bac(sm.snap[depth], &sm.tb);
+    Bac b = make_bac(sm.snap[depth]);
     if (pu) coder_reset(b.c);
     const int base_len = pu ? coder_len(b.c) : coder_len(sm.snap[depth]);
-    const Cx cx = {(u8*)(sm.lane_ctx + cand), 4 * NCAND};
     {
         const u32* src = (const u32*)(pu ? sm.ctx0 : sm.snap_ctx[depth]);
         u32* dst = sm.lane_ctx + cand;
@@ -996,21 +1059,21 @@ HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int cand, int dep
     } else {
         d.lev[0] = lev; d.mlo[0] = sm.cgnz[cand][0]; d.mhi = pu ? 0u : sm.cgnz[cand][1];
     }
-    code_cu(b, cx, d);
+    code_cu(b, sm_off(sm, sm.lane_ctx + cand), 4 * NCAND, d);
     sm.cand_bits[cand] = coder_len(b.c) - base_len;
     if (!pu) cand_coder(sm)[cand] = b.c;
 }
 
 // Evaluate the non-split candidates of one CU node and adopt the winner (HEVCe.c:1420-1559).
 template <int S>
-HEVCE_HD HEVCE_NOINLINE void eval_node(Shared& sm, const Scratch& sc, int q, int y0, int x0, const Avail& av, int depth) {
+HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0, const Avail& av, int depth) {
+    Shared& sm = my_sm();
     typedef Plan<S> P;
     constexpr int H = S / 2, N4 = S / 4, NSTEP = S == 8 ? 3 : 2;
     const RdK rk = rd_consts(q);
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
     const int gtL = S > sm.msz[my * 9 + mx - 1], gtA = S > sm.msz[(my - 1) * 9 + mx];
     const int pmL = sm.mpm[my * 9 + mx - 1], pmA = sm.mpm[(my - 1) * 9 + mx];
-    u8* pool = sm.pool;
 
     // split alternative: distortion of what the children left in the window (HEVCe.c:1409-1410)
     if (S > 8) {
@@ -1032,55 +1095,55 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(Shared& sm, const Scratch& sc, int q, int
             else { m0 = r * P::N0; n = imax(0, imin(P::N0, NMODE - m0)); }
             g0.n = n; g0.cand0 = m0; g0.mode0 = m0; g0.ty = y0; g0.tx = x0; g0.av = av; g0.priv = 0;
             g0.cuy = y0; g0.cux = x0; g0.cus = S; g0.tu = 0; g0.one_tu = 1; g0.grec = 1;
-            g0.blk = (s16*)(pool + P::BLK0); g0.pred = pool + P::PRED0; g0.psum = (int*)(pool + P::PSUM0); g0.bord = pool + P::BORD0;
-            g0.rec = nullptr; g0.rec_stride = 0; g0.rec_pitch = 0;
+            g0.blk = P::BLK0; g0.pred = P::PRED0; g0.psum = P::PSUM0; g0.bord = P::BORD0;
+            g0.rec = -1; g0.rec_stride = 0; g0.rec_pitch = 0;
         }
         {   // four-TU candidates: sub-TU k of a chunk of modes, each with its own reconstruction as neighbour
             const int m0 = chunk * P::N1, n = imax(0, imin(P::N1, NMODE - m0));
             g1.n = n; g1.cand0 = NMODE + m0; g1.mode0 = m0; g1.ty = y0 + (k >> 1) * H; g1.tx = x0 + (k & 1) * H; g1.av = sub_avail(av, k); g1.priv = 1;
             g1.cuy = y0; g1.cux = x0; g1.cus = S; g1.tu = k; g1.one_tu = 0; g1.grec = 1;
-            g1.blk = (s16*)(pool + P::BLK1); g1.pred = pool + P::PRED1; g1.psum = (int*)(pool + P::PSUM1); g1.bord = pool + P::BORD1;
-            g1.rec = pool + P::REC1; g1.rec_stride = S * S; g1.rec_pitch = S;
+            g1.blk = P::BLK1; g1.pred = P::PRED1; g1.psum = P::PSUM1; g1.bord = P::BORD1;
+            g1.rec = P::REC1; g1.rec_stride = S * S; g1.rec_pitch = S;
         }
         g2.n = 0;
         if (S == 8) {   // NxN PU k: all 35 modes, neighbours from the window (earlier PUs' winners are already there)
             g2.n = 35; g2.cand0 = 2 * NMODE; g2.mode0 = 0; g2.ty = y0 + (k >> 1) * 4; g2.tx = x0 + (k & 1) * 4; g2.av = sub_avail(av, k); g2.priv = 0;
             g2.cuy = g2.ty; g2.cux = g2.tx; g2.cus = 4; g2.tu = 0; g2.one_tu = 0; g2.grec = 0;
-            g2.blk = (s16*)(pool + P::BLK2); g2.pred = pool + P::PRED2; g2.psum = (int*)(pool + P::PSUM2); g2.bord = pool + P::BORD2;
-            g2.rec = pool + P::REC2; g2.rec_stride = 16; g2.rec_pitch = 4;
+            g2.blk = P::BLK2; g2.pred = P::PRED2; g2.psum = P::PSUM2; g2.bord = P::BORD2;
+            g2.rec = P::REC2; g2.rec_stride = 16; g2.rec_pitch = 4;
         }
         const int i0 = g0.n * S, i1 = g1.n * H;
         // ---- phase 0: reference samples
-        run_borders<S>(sm, g0, 0);
-        run_borders<H>(sm, g1, 2 * (4 * S + 1));
-        if (S == 8) run_borders<4>(sm, g2, 2 * (4 * S + 1) + g1.n * (4 * H + 1));
-        PHASE_END();
+        run_borders<S>(g0, 0);
+        run_borders<H>(g1, 2 * (4 * S + 1));
+        if (S == 8) run_borders<4>(g2, 2 * (4 * S + 1) + g1.n * (4 * H + 1));
+        PHASE_END_T(P_BORDER);
         // ---- phase A
-        if (g0.n) run_phase_a<S>(sm, g0, 0);
-        run_phase_a<H>(sm, g1, i0);
-        if (S == 8) run_phase_a<4>(sm, g2, i0 + i1);
-        PHASE_END();
+        if (g0.n) run_phase_a<S>(g0, 0);
+        run_phase_a<H>(g1, i0);
+        if (S == 8) run_phase_a<4>(g2, i0 + i1);
+        PHASE_END_T(P_A);
         // ---- phase B
-        if (g0.n) run_phase_b<S>(sm, g0, 0, q);
-        run_phase_b<H>(sm, g1, i0, q);
-        if (S == 8) run_phase_b<4>(sm, g2, i0 + i1, q);
-        PHASE_END();
+        if (g0.n) run_phase_b<S>(g0, 0, q);
+        run_phase_b<H>(g1, i0, q);
+        if (S == 8) run_phase_b<4>(g2, i0 + i1, q);
+        PHASE_END_T(P_B);
         // ---- phase C
-        if (g0.n) run_phase_c<S>(sm, sc, g0, 0, q);
-        run_phase_c<H>(sm, sc, g1, i0, q);
-        if (S == 8) run_phase_c<4>(sm, sc, g2, i0 + i1, q);
-        PHASE_END();
+        if (g0.n) run_phase_c<S>(sc, g0, 0, q);
+        run_phase_c<H>(sc, g1, i0, q);
+        if (S == 8) run_phase_c<4>(sc, g2, i0 + i1, q);
+        PHASE_END_T(P_C);
         // ---- phase D (+ the trial coders that only need the levels of phase C)
-        if (g0.n) run_phase_d<S>(sm, sc, g0, 0);
-        run_phase_d<H>(sm, sc, g1, i0);
+        if (g0.n) run_phase_d<S>(sc, g0, 0);
+        run_phase_d<H>(sc, g1, i0);
         if (S == 8) {
-            run_phase_d<4>(sm, sc, g2, i0 + i1);
+            run_phase_d<4>(sc, g2, i0 + i1);
             PAR_FOR(t, NT) {
                 const int cand = lane_to_cand(NSTEP, t);
                 if (cand >= 2 * NMODE || (cand >= 0 && r == 3)) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);
             }
         }
-        PHASE_END();
+        PHASE_END_T(P_D_TRIAL);
         if (S == 8) {
             PAR_FOR(one, 1) {   // best PU mode, last minimum wins (HEVCe.c:1521)
                 int best = IMAX, bm = 0;
@@ -1094,10 +1157,10 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(Shared& sm, const Scratch& sc, int q, int
                 const s16* lp = sc.glev + (size_t)ci * LEV_STRIDE;
                 for (int i = 0; i < 16; i++) {
                     sm.nxn_lev[k][i] = lp[i];
-                    HEVCE_WIN(sm, g2.ty + (i >> 2), g2.tx + (i & 3)) = g2.rec[bm * 16 + i];
+                    HEVCE_WIN(sm, g2.ty + (i >> 2), g2.tx + (i & 3)) = sm.pool[g2.rec + bm * 16 + i];
                 }
             }
-            PHASE_END();
+            PHASE_END_T(P_PU_ARGMIN);
         }
     }
 
@@ -1106,14 +1169,13 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(Shared& sm, const Scratch& sc, int q, int
             const int cand = lane_to_cand(NSTEP, t);
             if (cand >= 0) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);
         }
-        PHASE_END();
+        PHASE_END_T(P_TRIAL);
     }
 
     // ---- NxN as a whole + decision, reference order; every comparison is ">=" so the last minimum wins
     PAR_FOR(one, 1) {
         if (S == 8) {   // HEVCe.c:1531-1544
-            Bac b = make_bac(sm.snap[depth], &sm.tb);
-            const Cx cx = {sm.nxn_ctx, 4};
+            Bac b = make_bac(sm.snap[depth]);
             for (int i = 0; i < CTXW; i++) ((u32*)sm.nxn_ctx)[i] = ((const u32*)sm.snap_ctx[depth])[i];
             CuDesc d;
             d.s = S; d.kind = 2; d.split_ctx = gtL + gtA; d.mhi = 0;
@@ -1122,7 +1184,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(Shared& sm, const Scratch& sc, int q, int
             d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
             d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
             d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
-            code_cu(b, cx, d);
+            code_cu(b, sm_off(sm, sm.nxn_ctx), 4, d);
             int sse = 0;
             for (int y = 0; y < 8; y++)
                 for (int x = 0; x < 8; x++) { const int dd = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += dd * dd; }
@@ -1142,7 +1204,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(Shared& sm, const Scratch& sc, int q, int
         if (S == 8 && best >= sm.nxn_cost) win = NCAND;   // HEVCe.c:1546
         sm.win_item = win;
     }
-    PHASE_END();
+    PHASE_END_T(P_DECIDE);
     const int win = sm.win_item;   // < 0: the split stays: live state, window, levels and maps are already the children's
     // ---- adoption
     s16* clev = sc.ctu_lev + zoff(y0, x0);
@@ -1179,7 +1241,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(Shared& sm, const Scratch& sc, int q, int
         }
         PAR_FOR(one, 1) sm.live = cand_coder(sm)[win];
     }
-    PHASE_END();
+    PHASE_END_T(P_ADOPT);
 }
 
 // enter a node: snapshot the live state (HEVCe.c:1364-1365) and, for splittable nodes, code split_cu_flag = 1
@@ -1187,21 +1249,21 @@ template <int S>
 HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
     PAR_FOR(i, CTXW) ((u32*)sm.snap_ctx[depth])[i] = ((const u32*)sm.live_ctx)[i];
     PAR_FOR(one, 1) sm.snap[depth] = sm.live;
-    PHASE_END();
+    PHASE_END_T(P_ENTER);
     if (S > 8) {
         PAR_FOR(one, 1) {
             const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
-            Bac b = make_bac(sm.live, &sm.tb);
+            Bac b = make_bac(sm.live);
             const Cx cx = {sm.live_ctx, 4};
-            b.put_bin(1, cx[CX_SPLIT_CU + (S > sm.msz[my * 9 + mx - 1]) + (S > sm.msz[(my - 1) * 9 + mx])]);   // HEVCe.c:943-947
+            b.put_bin(sm.tb, 1, cx[CX_SPLIT_CU + (S > sm.msz[my * 9 + mx - 1]) + (S > sm.msz[(my - 1) * 9 + mx])]);   // HEVCe.c:943-947
             sm.live = b.c;
         }
-        PHASE_END();
+        PHASE_END_T(P_ENTER);
     }
 }
 
 // re-encode the decided CTU with the byte-writing coder (replaces the reference's per-trial byte buffers)
-HEVCE_HD inline void commit_cu(Bac& b, const Cx& cx, const Shared& sm, const s16* ctu_lev, int s, int y0, int x0) {
+HEVCE_HD inline void commit_cu(Bac& b, const Shared& sm, const s16* ctu_lev, int s, int y0, int x0) {
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4, h = s / 2;
     CuDesc d;
     d.s = s; d.kind = sm.kind[(y0 >> 3) * 4 + (x0 >> 3)]; d.split_ctx = -1; d.mhi = 0;
@@ -1218,22 +1280,22 @@ HEVCE_HD inline void commit_cu(Bac& b, const Cx& cx, const Shared& sm, const s16
     if (d.kind == 0) { d.lev[0] = lev; scan_groups(lev, s, d.mlo[0], d.mhi); }
     else
         for (int k = 0; k < 4; k++) { unsigned hi; d.lev[k] = lev + k * h * h; scan_groups(d.lev[k], h, d.mlo[k], hi); }
-    code_cu(b, cx, d);
+    code_cu(b, sm_off(sm, sm.start_ctx), 4, d);
 }
 
 HEVCE_HD inline void commit_ctu(Bac& b, const Cx& cx, const Shared& sm, const s16* lev) {
     auto gt = [&](int s, int y, int x) { return (s > sm.msz[(1 + y / 4) * 9 + 1 + x / 4 - 1]) + (s > sm.msz[(1 + y / 4 - 1) * 9 + 1 + x / 4]); };
     const int whole = sm.msz[10] == 32;
-    b.put_bin(!whole, cx[CX_SPLIT_CU + gt(32, 0, 0)]);
-    if (whole) { commit_cu(b, cx, sm, lev, 32, 0, 0); return; }
+    b.put_bin(sm.tb, !whole, cx[CX_SPLIT_CU + gt(32, 0, 0)]);
+    if (whole) { commit_cu(b, sm, lev, 32, 0, 0); return; }
     for (int a = 0; a < 4; a++) {
         const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
         const int sz = sm.msz[(1 + y16 / 4) * 9 + 1 + x16 / 4];
-        b.put_bin(sz != 16, cx[CX_SPLIT_CU + gt(16, y16, x16)]);
+        b.put_bin(sm.tb, sz != 16, cx[CX_SPLIT_CU + gt(16, y16, x16)]);
         const int ncu = sz == 16 ? 1 : 4;
         for (int c = 0; c < ncu; c++) {
-            if (sz == 16) commit_cu(b, cx, sm, lev, 16, y16, x16);
-            else commit_cu(b, cx, sm, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
+            if (sz == 16) commit_cu(b, sm, lev, 16, y16, x16);
+            else commit_cu(b, sm, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
         }
     }
 }
@@ -1281,7 +1343,7 @@ HEVCE_HD inline int write_header(u8* out, int q, int H, int W) {
 HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared& sm, const Scratch& sc) {
     const int q = job.q, H = job.H, W = job.W;
     PAR_FOR(i, (int)(sizeof(Tables) / 4)) ((u32*)&sm.tb)[i] = ((const u32*)&tables)[i];
-    PHASE_END();
+    PHASE_END_T(P_MISC);
     PAR_FOR(i, 144) {
         const u8 v = i < NCTX ? ctx_init_value(sm.tb.ctx_iv[i], q) : (u8)0;
         sm.ctx0[i] = v;
@@ -1298,7 +1360,7 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
         sm.error = 0;
         sm.stream_pos = write_header(job.out, q, H, W);
     }
-    PHASE_END();
+    PHASE_END_T(P_MISC);
 
     for (int cy = 0; cy < H; cy += CTU) {
         for (int cx = 0; cx < W; cx += CTU) {
@@ -1318,7 +1380,7 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
             }
             PAR_FOR(i, CTXW) ((u32*)sm.start_ctx)[i] = ((const u32*)sm.live_ctx)[i];
             PAR_FOR(one, 1) { sm.live.n = 0; sm.start = sm.live; }
-            PHASE_END();
+            PHASE_END_T(P_LOAD);
 
             // ---- CU quadtree, z-order, children before the parent's own candidates (HEVCe.c:1403-1413)
             enter_node<32>(sm, 0, 0, 0);
@@ -1329,21 +1391,21 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
                 for (int c = 0; c < 4; c++) {
                     const int y8 = y16 + (c >> 1) * 8, x8 = x16 + (c & 1) * 8;
                     enter_node<8>(sm, y8, x8, 2);
-                    eval_node<8>(sm, sc, q, y8, x8, sub_avail(av16, c), 2);
+                    eval_node<8>(sc, q, y8, x8, sub_avail(av16, c), 2);
                 }
-                eval_node<16>(sm, sc, q, y16, x16, av16, 1);
+                eval_node<16>(sc, q, y16, x16, av16, 1);
             }
-            eval_node<32>(sm, sc, q, 0, 0, av, 0);
+            eval_node<32>(sc, q, 0, 0, av, 0);
 
             // ---- store reconstruction + map row, terminate bin, commit the CTU's bytes
             PAR_FOR(i, CTU * CTU) job.rcon[(size_t)(cy + i / CTU) * W + cx + i % CTU] = HEVCE_WIN(sm, i / CTU, i % CTU);
             PAR_FOR(i, 8) sc.msz_line[cx / 4 + i] = sm.msz[8 * 9 + 1 + i];
             PAR_FOR(one, 1) {
                 const int last = cy + CTU >= H && cx + CTU >= W;
-                Bac t = make_bac(sm.live, &sm.tb);
+                Bac t = make_bac(sm.live);
                 t.put_terminate(last);                                                  // HEVCe.c:1630
                 if (last) t.finish();                                                   // HEVCe.c:1640
-                Bac b = make_bac(sm.start, &sm.tb);
+                Bac b = make_bac(sm.start);
                 b.out = job.out + sm.stream_pos;
                 b.cap = imax(0, job.out_cap - sm.stream_pos);
                 const Cx cxs = {sm.start_ctx, 4};
@@ -1356,14 +1418,14 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
                 sm.stream_pos += b.c.n;
                 sm.live = t.c;
             }
-            PHASE_END();
+            PHASE_END_T(P_COMMIT);
         }
     }
     PAR_FOR(one, 1) {
         job.result[0] = sm.stream_pos;
         job.result[1] = sm.error;
     }
-    PHASE_END();
+    PHASE_END_T(P_MISC);
 }
 
 }   // namespace hevce

@@ -35,14 +35,19 @@ using namespace hevce;
 // kernels
 // ------------------------------------------------------------------------------------------------------------
 __device__ Tables g_tables;
+#if defined(HEVCE_PROFILE)
+namespace hevce {
+__device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_phase_count[16];
+}
+#endif
 
 // A CTA = GANG pictures of identical padded size, one per group of NT threads.  `gangs` lists GANG job indices per
 // work unit (a short gang repeats its first job: the duplicate writes identical bytes).
 __global__ void __launch_bounds__(NT * GANG, 1)
 hevce_encode_kernel(const Job* __restrict__ jobs, const int* __restrict__ gangs, int ngangs, const Scratch* __restrict__ slots, int* counter) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int member = threadIdx.x / NT;
-    Shared& sm = reinterpret_cast<Shared*>(smem_raw)[member];
+    Shared& sm = my_sm();
     __shared__ int s_next;
     const Scratch sc = slots[blockIdx.x * GANG + member];
     for (;;) {
@@ -353,6 +358,19 @@ extern "C" void hevce_session_destroy(hevce_session* s) {
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
+
+#if defined(HEVCE_PROFILE)
+extern "C" __attribute__((visibility("default"))) void hevce_profile_dump(void) {
+    unsigned long long c[16], n[16];
+    cudaMemcpyFromSymbol(c, g_phase_cycles, sizeof c);
+    cudaMemcpyFromSymbol(n, g_phase_count, sizeof n);
+    static const char* names[] = {"border", "A", "B", "C", "D+pu/trial", "pu_argmin", "trial(S>8)", "decide", "adopt", "enter", "load", "commit", "misc"};
+    unsigned long long tot = 0;
+    for (int i = 0; i < P_NTAGS; i++) tot += c[i];
+    for (int i = 0; i < P_NTAGS; i++)
+        printf("phase %-12s count %10llu cycles %14llu  %5.1f%%  avg %8.0f\n", names[i], n[i], c[i], 100.0 * c[i] / (double)tot, n[i] ? (double)c[i] / n[i] : 0.0);
+}
+#endif
 
 extern "C" int hevce_internal_device_count(void) {
     int n = 0;

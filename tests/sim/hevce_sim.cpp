@@ -8,7 +8,7 @@
 
 #include "hevce_core.h"
 
-namespace hevce { int g_sim_order = 0; }
+namespace hevce { int g_sim_order = 0; Shared* g_sim_sm = nullptr; }
 
 extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned char* img, unsigned char* rcon,
                                 int* ysz, int* xsz, int q, int order, int max_dim, int* err) {
@@ -29,6 +29,7 @@ extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned 
     sc.glev = glev.data(); sc.grec = grec.data(); sc.ctu_lev = lev.data(); sc.msz_line = line.data();
     Shared* sm = new Shared;
     memset(sm, 0xA5, sizeof(Shared));   // shared memory is not zeroed on the GPU either
+    g_sim_sm = sm;
     encode_picture(job, tables, *sm, sc);
     delete sm;
     *ysz = job.H; *xsz = job.W;

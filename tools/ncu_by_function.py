@@ -55,10 +55,17 @@ def fn(line):
     return name
 
 
+stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+fstall = collections.defaultdict(collections.Counter)
 agg, samp, cnt, thr = (collections.Counter() for _ in range(4))
 for k in range(min(len(ins), len(data))):
     key = ins[k] or ("?", 0)
     agg[key] += int(data[k][ix]); samp[key] += int(data[k][isamp]); cnt[key] += 1; thr[key] += int(data[k][ithr])
+    fk = (key[0], fn(key[1])) if key[0] == "hevce_core.h" else (key[0], "-")
+    for ci in stall_cols:
+        v = int(data[k][ci] or 0)
+        if v:
+            fstall[fk][hdr[ci][6:]] += v
 tot, ts = sum(agg.values()), sum(samp.values())
 print("warp instructions", tot, "samples", ts, "avg active threads %.1f" % (sum(thr.values()) / max(tot, 1)))
 fa, fs, fc, ft = (collections.Counter() for _ in range(4))
@@ -67,7 +74,8 @@ for (f, ln), v in agg.items():
     fa[k] += v; fs[k] += samp[(f, ln)]; fc[k] += cnt[(f, ln)]; ft[k] += thr[(f, ln)]
 print("%inst %samples  #sass  thr/inst  function")
 for k, v in fa.most_common(28):
-    print(f"{v / tot * 100:5.1f} {fs[k] / ts * 100:7.1f} {fc[k]:7d} {ft[k] / max(v, 1):8.1f}  {k[0]}:{k[1]}")
+    top = ", ".join(f"{n}:{c / max(fs[k], 1) * 100:.0f}%" for n, c in fstall[k].most_common(4))
+    print(f"{v / tot * 100:5.1f} {fs[k] / ts * 100:7.1f} {fc[k]:7d} {ft[k] / max(v, 1):8.1f}  {k[0]}:{k[1]:16s} {top}")
 print("top lines")
 for k, v in agg.most_common(22):
     s = src[k[1] - 1].strip()[:100] if k[0] == "hevce_core.h" and k[1] <= len(src) else ""
