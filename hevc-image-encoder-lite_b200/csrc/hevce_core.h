@@ -383,8 +383,10 @@ HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CO
 #if defined(__CUDA_ARCH__)
 extern __shared__ __align__(16) unsigned char hevce_smem[];
 __device__ __forceinline__ Shared& my_sm() { return reinterpret_cast<Shared*>(hevce_smem)[threadIdx.x / NT]; }
+#elif defined(__CUDACC__)
+inline Shared& my_sm() { return *static_cast<Shared*>(nullptr); }   // host pass of nvcc: declared, never executed
 #else
-extern Shared* g_sim_sm;
+extern Shared* g_sim_sm;                                             // CTA simulator (tests/sim)
 inline Shared& my_sm() { return *g_sim_sm; }
 #endif
 static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail too small");
