@@ -967,31 +967,38 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
 
 // phase runners: one (non-inlined) copy per TU size, shared by all node sizes
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_borders(const Grp& g, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_borders(const Grp& gref, int off) {
     Shared& sm = my_sm();
+    const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
     if (g.n == 0) return;
     const int n = (g.priv ? g.n : (T > 4 ? 2 : 1)) * (4 * T + 1);
     PAR_FOR_OFF(item, n, off) border_item<T>(sm, g, item);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_a(const Grp& g, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_a(const Grp& gref, int off) {
     Shared& sm = my_sm();
+    const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
     PAR_FOR_OFF(item, g.n * T, off) phase_a_item<T>(sm, g, item);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_b(const Grp& g, int off, int q) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_b(const Grp& gref, int off, int q) {
     Shared& sm = my_sm();
+    const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
     const RdK rk = rd_consts(q);
     PAR_FOR_OFF(item, g.n * T, off) phase_b_item<T>(sm, g, item, q, rk);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_c(const Scratch& sc, const Grp& g, int off, int q) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_c(const Scratch& scref, const Grp& gref, int off, int q) {
     Shared& sm = my_sm();
+    const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
+    const Scratch sc = scref;
     PAR_FOR_OFF(item, g.n * T, off) phase_c_item<T>(sm, sc, g, item, q);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& sc, const Grp& g, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, int off) {
     Shared& sm = my_sm();
+    const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
+    const Scratch sc = scref;
     PAR_FOR_OFF(item, g.n * T, off) phase_d_item<T>(sm, sc, g, item);
 }
 
@@ -1142,7 +1149,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             run_phase_d<4>(sc, g2, i0 + i1);
             PAR_FOR(t, NT) {
                 const int cand = lane_to_cand(NSTEP, t);
-                if (cand >= 2 * NMODE || (cand >= 0 && r == 3)) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);
+                if (cand >= 2 * NMODE) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);   // NxN PU modes of this round
             }
         }
         PHASE_END_T(P_D_TRIAL);
@@ -1166,17 +1173,11 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         }
     }
 
-    if (S > 8) {   // all 70 trial coders of a 16x16 / 32x32 node
-        PAR_FOR(t, NT) {
-            const int cand = lane_to_cand(NSTEP, t);
-            if (cand >= 0) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);
-        }
-        PHASE_END_T(P_TRIAL);
-    }
-
-    // ---- NxN as a whole + decision, reference order; every comparison is ">=" so the last minimum wins
-    PAR_FOR(one, 1) {
-        if (S == 8) {   // HEVCe.c:1531-1544
+    // ---- all 70 one-TU / four-TU trial coders; for 8x8 nodes a spare thread codes the NxN CU as a whole meanwhile
+    PAR_FOR(t, NT) {
+        const int cand = lane_to_cand(2, t);
+        if (cand >= 0) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);
+        else if (S == 8 && t == NT - 1) {   // HEVCe.c:1531-1544
             Bac b = make_bac(sm.snap[depth]);
             for (int i = 0; i < CTXW; i++) ((u32*)sm.nxn_ctx)[i] = ((const u32*)sm.snap_ctx[depth])[i];
             CuDesc d;
@@ -1193,6 +1194,11 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             sm.nxn_cost = rd_cost(rk, sse, coder_len(b.c) - coder_len(sm.snap[depth]));
             sm.nxn_coder = b.c;
         }
+    }
+    PHASE_END_T(P_TRIAL);
+
+    // ---- decision, reference order; every comparison is ">=" so the last minimum wins
+    PAR_FOR(one, 1) {
         int best = IMAX, win = -1;
         if (S > 8) {
             int sse = 0;
