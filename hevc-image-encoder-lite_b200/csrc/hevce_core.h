@@ -199,21 +199,28 @@ HEVCE_HD inline bool coder_equal(const Coder& a, const Coder& b) {
     return a.range == b.range && a.low == b.low && a.nbits == b.nbits && a.nbytes == b.nbytes && a.held == b.held && a.z == b.z && a.n == b.n;
 }
 
-struct Bac {
+template <bool EMIT>
+struct BacT {
     Coder c;
-    u8* out;            // commit only: destination of this CTU's bytes (nullptr for trials)
-    int cap;            // commit only: bytes available at out
+    u8* out;            // EMIT only: destination of this CTU's bytes
+    int cap;            // EMIT only: bytes available at out
 
     HEVCE_HD void emit(int byte) {   // HEVCe.c:821-832
         const int b = byte & 0xff;
-        if (c.z >= 2 && b <= 3) {
-            if (out && c.n < cap) out[c.n] = 3;
+        if (EMIT) {
+            if (c.z >= 2 && b <= 3) {
+                if (c.n < cap) out[c.n] = 3;
+                c.n++;
+                c.z = 0;
+            }
+            if (c.n < cap) out[c.n] = (u8)b;
             c.n++;
-            c.z = 0;
+            c.z = b ? 0 : c.z + 1;
+        } else {   // trial: count only, branch-free
+            const int epb = (c.z >= 2) & (b <= 3);
+            c.n += 1 + epb;
+            c.z = b ? 0 : (epb ? 1 : c.z + 1);
         }
-        if (out && c.n < cap) out[c.n] = (u8)b;
-        c.n++;
-        c.z = b ? 0 : c.z + 1;
     }
     HEVCE_HD void carry_out() {   // HEVCe.c:859-879
         if (c.nbits >= 12) return;
@@ -228,20 +235,18 @@ struct Bac {
             for (; c.nbytes > 1; c.nbytes--) emit((0xff + carry) & 0xff);
         } else { c.nbytes = 1; c.held = lead; }
     }
-    HEVCE_HD void put_bin(const Tables& tb, int bin, u8& cx) {   // HEVCe.c:914-933
+    HEVCE_HD void put_bin(const Tables& tb, int bin, u8& cx) {   // HEVCe.c:914-933, both branches computed, then selected
         const int v = cx;
         const int lps = tb.lps[(v >> 1) * 4 + ((c.range >> 6) & 3)];
-        c.range -= lps;
-        if ((bin != 0) != (v & 1)) {
-            const int nb = lps < 8 ? 6 : 9 - bitlen((unsigned)lps);   // renorm table, HEVCe.c:715
-            cx = tb.next_lps[v];
-            c.low = (int)((unsigned)(c.low + c.range) << nb);
-            c.range = lps << nb;
-            c.nbits -= nb;
-        } else {
-            cx = (u8)(v < 124 ? v + 2 : v);                            // HEVCe.c:701
-            if (c.range < 256) { c.low = (int)((unsigned)c.low << 1); c.range <<= 1; c.nbits--; }
-        }
+        const int nlps = tb.next_lps[v];
+        const int rmps = c.range - lps;
+        const bool is_lps = (bin != 0) != ((v & 1) != 0);
+        const int nb = lps < 8 ? 6 : 9 - bitlen((unsigned)lps);     // renorm table, HEVCe.c:715
+        const int sh = is_lps ? nb : (rmps < 256 ? 1 : 0);
+        c.low = (int)((unsigned)(is_lps ? c.low + rmps : c.low) << sh);
+        c.range = (is_lps ? lps : rmps) << sh;
+        c.nbits -= sh;
+        cx = (u8)(is_lps ? nlps : (v < 124 ? v + 2 : v));           // HEVCe.c:701-702
         carry_out();
     }
     HEVCE_HD void put_bypass(int bins, int len) {   // HEVCe.c:899-911
@@ -270,6 +275,8 @@ struct Bac {
         emit(t >> 16); emit(t >> 8); emit(t);
     }
 };
+typedef BacT<false> Bac;        // trial coder: full integer state, no byte store
+typedef BacT<true> BacCommit;   // commit coder: writes the CTU's bytes
 
 // context set: byte k at base[(k>>2)*s4 + (k&3)].  s4 = 4: plain array; s4 = 4*NCAND: lane-private column of the
 // word-interleaved shared-memory array (every lane owns one bank).  The base pointer is always derived from the
@@ -460,7 +467,8 @@ HEVCE_HD inline void load_group(const s16* p, u32 (&w)[8]) {
 
 // one coefficient group: bit-fields in scan order, last position (first coded group only), sig flags, greater1/2,
 // signs, remaining levels.  w: the 16 levels (8 words), gp: the same group in the store (escape magnitudes).
-HEVCE_HD inline void code_group(Bac& b, const Tables& tbl, const Cx cx, int s, int st, int lg, int sigbase, const s16* gp, const u32 (&w)[8],
+template <class BAC>
+HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, int st, int lg, int sigbase, const s16* gp, const u32 (&w)[8],
                                 int on, int pat, int first_cg, bool is_last, int cy, int cxg, int& c1) {
     const Tables* tb = &tbl;
     // ---- bit-fields of the group, scan order
@@ -569,7 +577,8 @@ HEVCE_HD inline void code_group(Bac& b, const Tables& tbl, const Cx cx, int s, i
 // bitmap of non-zero 4x4 groups (bit gy*8+gx), so all-zero groups cost one bin and no memory traffic; a coded group
 // is reduced to three bit-fields in scan order (non-zero mask, signs, min(|level|,3) classes) that drive every
 // context-coded bin; only escape magnitudes are read back from the store.
-HEVCE_HD inline void put_residual(Bac& b, const Tables& tbl, const Cx cx, int s, int m, const s16* lev, unsigned mlo, unsigned mhi) {
+template <class BAC>
+HEVCE_HD inline void put_residual(BAC& b, const Tables& tbl, const Cx cx, int s, int m, const s16* lev, unsigned mlo, unsigned mhi) {
     const Tables* tb = &tbl;
     const int st = scan_type(s, m), lg = ilog2(s), ncg = s >> 2;
     const int sigbase = CX_SIG + 9 + (s >= 16 ? 12 : 0) + ((s == 8 && st) ? 6 : 0);
@@ -634,11 +643,12 @@ struct CuDesc {
     unsigned mhi;
 };
 
-HEVCE_HD HEVCE_NOINLINE void code_cu(Bac& bio, int cx_off, int cx_s4, const CuDesc& d) {
+template <class BAC>
+HEVCE_HD HEVCE_NOINLINE void code_cu(BAC& bio, int cx_off, int cx_s4, const CuDesc& d) {
     Shared& sm = my_sm();
     const Tables& tbl = sm.tb;
     const Cx cx = {(u8*)&sm + cx_off, cx_s4};
-    Bac b = bio;   // coder state in registers for the whole CU
+    BAC b = bio;   // coder state in registers for the whole CU
     const int s = d.s, kind = d.kind;
     if (kind != 3) {
         if (d.split_ctx >= 0 && s >= 16) b.put_bin(tbl, 0, cx[CX_SPLIT_CU + d.split_ctx]);
@@ -864,17 +874,17 @@ HEVCE_HD inline void phase_b_item(Shared& sm, const Grp& g, int item, int q, con
             const int x = gx * 4 + e;
             const int cf = bp[x];
             const int dl = iabs(cf) << 14;                       // |cf| <= 32640: the clamps of HEVCe.c:566 cannot trigger
-            int lvl = (dl + add) >> sh;
-            int pick = 0;
-            if (lvl > 0) {
-                const int lo = imax(0, lvl - 2);
-                int best = IMAX;
-                for (; lvl >= lo; lvl--) {
-                    const int d1 = iabs(dl - (lvl << sh)) >> dsh;
+            const int lvl = (dl + add) >> sh;
+            if (lvl > 0) {   // candidates lvl, lvl-1, lvl-2 (>= 0); strict '<' scanning downwards: the highest level wins ties
+                int pick = lvl, best = IMAX;
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const int l = lvl - t;
+                    const int d1 = iabs(dl - (l << sh)) >> dsh;
                     const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
-                    const int wr = lvl < 6 ? sm.rate6[lvl] : wb * (92000 + ((4 + 2 * (bitlen((unsigned)(lvl - 5)) - 1)) << 15));   // HEVCe.c:526-535
+                    const int wr = l < 6 ? sm.rate6[imax(l, 0)] : wb * (92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15));   // HEVCe.c:526-535
                     const int cost = wd * d + wr;
-                    if (cost < best) { best = cost; pick = lvl; }
+                    if (l >= 0 && cost < best) { best = cost; pick = l; }
                 }
                 bp[x] = (s16)(cf < 0 ? -pick : pick);
             } else bp[x] = 0;
@@ -1271,7 +1281,7 @@ HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
 }
 
 // re-encode the decided CTU with the byte-writing coder (replaces the reference's per-trial byte buffers)
-HEVCE_HD inline void commit_cu(Bac& b, const Shared& sm, const s16* ctu_lev, int s, int y0, int x0) {
+HEVCE_HD inline void commit_cu(BacCommit& b, const Shared& sm, const s16* ctu_lev, int s, int y0, int x0) {
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4, h = s / 2;
     CuDesc d;
     d.s = s; d.kind = sm.kind[(y0 >> 3) * 4 + (x0 >> 3)]; d.split_ctx = -1; d.mhi = 0;
@@ -1291,7 +1301,7 @@ HEVCE_HD inline void commit_cu(Bac& b, const Shared& sm, const s16* ctu_lev, int
     code_cu(b, sm_off(sm, sm.start_ctx), 4, d);
 }
 
-HEVCE_HD inline void commit_ctu(Bac& b, const Cx& cx, const Shared& sm, const s16* lev) {
+HEVCE_HD inline void commit_ctu(BacCommit& b, const Cx& cx, const Shared& sm, const s16* lev) {
     auto gt = [&](int s, int y, int x) { return (s > sm.msz[(1 + y / 4) * 9 + 1 + x / 4 - 1]) + (s > sm.msz[(1 + y / 4 - 1) * 9 + 1 + x / 4]); };
     const int whole = sm.msz[10] == 32;
     b.put_bin(sm.tb, !whole, cx[CX_SPLIT_CU + gt(32, 0, 0)]);
@@ -1413,7 +1423,8 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
                 Bac t = make_bac(sm.live);
                 t.put_terminate(last);                                                  // HEVCe.c:1630
                 if (last) t.finish();                                                   // HEVCe.c:1640
-                Bac b = make_bac(sm.start);
+                BacCommit b;
+                b.c = sm.start;
                 b.out = job.out + sm.stream_pos;
                 b.cap = imax(0, job.out_cap - sm.stream_pos);
                 const Cx cxs = {sm.start_ctx, 4};
