@@ -329,7 +329,18 @@ HEVCE_HD inline int intra_angle(int m) {   // HEVCe.c:282
 // ------------------------------------------------------------------------------------------------------------
 // picture-level state
 // ------------------------------------------------------------------------------------------------------------
+struct CtuRec {          // what the commit pass needs for one CTU (written by the decision kernel)
+    Coder start, end;    // coder state before the CTU / after its terminate bin (and the final flush for the last CTU)
+    int out_pos;         // byte offset of this CTU's bytes in the stream
+    int last;            // 1: last CTU of the picture
+    u8 ctx[144];         // contexts at CTU start
+    u8 msz[84], mpm[84]; // neighbour maps after the CTU was decided ([1+uy][1+ux], 81 used)
+    u8 kind[16];
+};
+
 struct Job {
+    CtuRec* recs;      // one record per CTU, raster order
+    s16* levs;         // CTU*CTU final levels per CTU: CUs at their z-order offset, group-blocked
     const u8* img;     // source picture (device), stride src_w
     u8* rcon;          // reconstruction (device), H x W
     u8* out;           // bitstream (device)
@@ -349,7 +360,6 @@ constexpr int NREC = 70;                // candidates whose reconstruction is ke
 struct Scratch {       // per picture slot, global memory (L2-resident working set)
     s16* glev;         // [NCAND][LEV_STRIDE] final levels of every candidate of the current node (group-blocked)
     u8* grec;          // [NREC][CTU*CTU] reconstruction of every non-NxN candidate, CU-local raster
-    s16* ctu_lev;      // CTU*CTU final levels of the current CTU: CUs at their z-order offset, group-blocked
     u8* msz_line;      // CU-size map row of the CTU row above, W/4 entries
 };
 
@@ -363,14 +373,14 @@ struct Shared {
     alignas(16) u8 ctx0[144];           // freshly initialised contexts for this picture's qpd6
     alignas(16) u8 live_ctx[144];
     alignas(16) u8 snap_ctx[3][144];
-    alignas(16) u8 start_ctx[144];
     alignas(16) u8 nxn_ctx[144];
     alignas(16) s16 nxn_lev[4][16];
     u8 orig[CTU * CTU];
     u8 win[(CTU + 1) * WP];
     u8 msz[81], mpm[81];                // [1+uy][1+ux], 4x4 units; row 0 / col 0 = neighbours
     u8 kind[16];                        // per 8x8 unit: 0 one TU, 1 four TUs, 2 NxN
-    Coder live, snap[3], start, nxn_coder;
+    Coder live, snap[3], nxn_coder;
+    s16* ctu_lev;                       // level store of the current CTU (Job::levs + ctu*1024)
     int cand_sse[NCAND], cand_bits[NCAND];
     unsigned cgnz[NCAND][4];            // non-zero-group bitmaps: one-TU: [0],[1] = low/high word; else [tu]
     int rate6[6];                       // RDOQ: weighted rate of levels 0..5
@@ -632,6 +642,29 @@ HEVCE_HD inline void put_residual(BAC& b, const Tables& tbl, const Cx cx, int s,
     }
 }
 
+// Where tables and context sets live: the decision kernel keeps them in the picture's Shared block, the commit kernel
+// in its own small shared block.  Both are reached through the extern shared array so the accesses stay LDS/STS.
+struct CommitShared {
+    Tables tb;
+    u32 ctx[CTXW * NT];   // lane-private context sets of the NT commit threads of a block, word-interleaved
+};
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ CommitShared& my_csm() { return *reinterpret_cast<CommitShared*>(hevce_smem); }
+#elif defined(__CUDACC__)
+inline CommitShared& my_csm() { return *static_cast<CommitShared*>(nullptr); }
+#else
+extern CommitShared* g_sim_csm;
+inline CommitShared& my_csm() { return *g_sim_csm; }
+#endif
+struct MainEnv {
+    HEVCE_HD static const Tables& tables() { return my_sm().tb; }
+    HEVCE_HD static u8* base() { return (u8*)&my_sm(); }
+};
+struct CommitEnv {
+    HEVCE_HD static const Tables& tables() { return my_csm().tb; }
+    HEVCE_HD static u8* base() { return (u8*)&my_csm(); }
+};
+
 // One coding unit (HEVCe.c:1272-1340, 943-947).
 struct CuDesc {
     int s;              // CU size
@@ -643,11 +676,10 @@ struct CuDesc {
     unsigned mhi;
 };
 
-template <class BAC>
+template <class BAC, class ENV>
 HEVCE_HD HEVCE_NOINLINE void code_cu(BAC& bio, int cx_off, int cx_s4, const CuDesc& d) {
-    Shared& sm = my_sm();
-    const Tables& tbl = sm.tb;
-    const Cx cx = {(u8*)&sm + cx_off, cx_s4};
+    const Tables& tbl = ENV::tables();
+    const Cx cx = {ENV::base() + cx_off, cx_s4};
     BAC b = bio;   // coder state in registers for the whole CU
     const int s = d.s, kind = d.kind;
     if (kind != 3) {
@@ -1078,7 +1110,7 @@ HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int cand, int dep
     } else {
         d.lev[0] = lev; d.mlo[0] = sm.cgnz[cand][0]; d.mhi = pu ? 0u : sm.cgnz[cand][1];
     }
-    code_cu(b, sm_off(sm, sm.lane_ctx + cand), 4 * NCAND, d);
+    code_cu<Bac, MainEnv>(b, sm_off(sm, sm.lane_ctx + cand), 4 * NCAND, d);
     sm.cand_bits[cand] = coder_len(b.c) - base_len;
     if (!pu) cand_coder(sm)[cand] = b.c;
 }
@@ -1197,7 +1229,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
             d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
             d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
-            code_cu(b, sm_off(sm, sm.nxn_ctx), 4, d);
+            code_cu<Bac, MainEnv>(b, sm_off(sm, sm.nxn_ctx), 4, d);
             int sse = 0;
             for (int y = 0; y < 8; y++)
                 for (int x = 0; x < 8; x++) { const int dd = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += dd * dd; }
@@ -1225,7 +1257,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
     PHASE_END_T(P_DECIDE);
     const int win = sm.win_item;   // < 0: the split stays: live state, window, levels and maps are already the children's
     // ---- adoption
-    s16* clev = sc.ctu_lev + zoff(y0, x0);
+    s16* clev = sm.ctu_lev + zoff(y0, x0);
     if (win < 0) {
         // nothing to adopt; still take the barrier below (all pictures of a CTA keep the same barrier sequence)
     } else if (win == NCAND) {
@@ -1280,42 +1312,66 @@ HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
     }
 }
 
-// re-encode the decided CTU with the byte-writing coder (replaces the reference's per-trial byte buffers)
-HEVCE_HD inline void commit_cu(BacCommit& b, const Shared& sm, const s16* ctu_lev, int s, int y0, int x0) {
+// Commit pass: re-encode one decided CTU with the byte-writing coder from its recorded start state (replaces the
+// reference's per-trial byte buffers).  One thread per CTU in hevce_commit_kernel; CTUs are independent here because
+// the decision kernel recorded every CTU's start state and byte offset.
+HEVCE_HD inline void commit_cu(BacCommit& b, int cx_off, int cx_s4, const CtuRec& r, const s16* ctu_lev, int s, int y0, int x0) {
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4, h = s / 2;
     CuDesc d;
-    d.s = s; d.kind = sm.kind[(y0 >> 3) * 4 + (x0 >> 3)]; d.split_ctx = -1; d.mhi = 0;
-    d.pm[0] = sm.mpm[my * 9 + mx];
-    d.pl[0] = sm.mpm[my * 9 + mx - 1];
-    d.pa[0] = sm.mpm[(my - 1) * 9 + mx];
+    d.s = s; d.kind = r.kind[(y0 >> 3) * 4 + (x0 >> 3)]; d.split_ctx = -1; d.mhi = 0;
+    d.pm[0] = r.mpm[my * 9 + mx];
+    d.pl[0] = r.mpm[my * 9 + mx - 1];
+    d.pa[0] = r.mpm[(my - 1) * 9 + mx];
     if (d.kind == 2) {
-        d.pm[1] = sm.mpm[my * 9 + mx + 1]; d.pm[2] = sm.mpm[(my + 1) * 9 + mx]; d.pm[3] = sm.mpm[(my + 1) * 9 + mx + 1];
-        d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
-        d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
+        d.pm[1] = r.mpm[my * 9 + mx + 1]; d.pm[2] = r.mpm[(my + 1) * 9 + mx]; d.pm[3] = r.mpm[(my + 1) * 9 + mx + 1];
+        d.pl[1] = d.pm[0]; d.pa[1] = r.mpm[(my - 1) * 9 + mx + 1];
+        d.pl[2] = r.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
         d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
     }
     const s16* lev = ctu_lev + zoff(y0, x0);
     if (d.kind == 0) { d.lev[0] = lev; scan_groups(lev, s, d.mlo[0], d.mhi); }
     else
         for (int k = 0; k < 4; k++) { unsigned hi; d.lev[k] = lev + k * h * h; scan_groups(d.lev[k], h, d.mlo[k], hi); }
-    code_cu(b, sm_off(sm, sm.start_ctx), 4, d);
+    code_cu<BacCommit, CommitEnv>(b, cx_off, cx_s4, d);
 }
 
-HEVCE_HD inline void commit_ctu(BacCommit& b, const Cx& cx, const Shared& sm, const s16* lev) {
-    auto gt = [&](int s, int y, int x) { return (s > sm.msz[(1 + y / 4) * 9 + 1 + x / 4 - 1]) + (s > sm.msz[(1 + y / 4 - 1) * 9 + 1 + x / 4]); };
-    const int whole = sm.msz[10] == 32;
-    b.put_bin(sm.tb, !whole, cx[CX_SPLIT_CU + gt(32, 0, 0)]);
-    if (whole) { commit_cu(b, sm, lev, 32, 0, 0); return; }
-    for (int a = 0; a < 4; a++) {
-        const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
-        const int sz = sm.msz[(1 + y16 / 4) * 9 + 1 + x16 / 4];
-        b.put_bin(sm.tb, sz != 16, cx[CX_SPLIT_CU + gt(16, y16, x16)]);
-        const int ncu = sz == 16 ? 1 : 4;
-        for (int c = 0; c < ncu; c++) {
-            if (sz == 16) commit_cu(b, sm, lev, 16, y16, x16);
-            else commit_cu(b, sm, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
+HEVCE_HD inline void commit_ctu(const Job& job, int ctu, int lane) {
+    CommitShared& cs = my_csm();
+    const CtuRec& r = job.recs[ctu];
+    const s16* lev = job.levs + (size_t)ctu * (CTU * CTU);
+    u32* cw = cs.ctx + lane;
+    for (int k = 0; k < CTXW; k++) cw[k * NT] = ((const u32*)r.ctx)[k];
+    const int cx_off = (int)((u8*)cw - (u8*)&cs), cx_s4 = 4 * NT;
+    const Cx cx = {(u8*)cw, cx_s4};
+    BacCommit b;
+    b.c = r.start;
+    b.out = job.out + r.out_pos;
+    b.cap = imax(0, job.out_cap - r.out_pos);
+    auto gt = [&](int s, int y, int x) { return (s > r.msz[(1 + y / 4) * 9 + 1 + x / 4 - 1]) + (s > r.msz[(1 + y / 4 - 1) * 9 + 1 + x / 4]); };
+    const int whole = r.msz[10] == 32;
+    b.put_bin(cs.tb, !whole, cx[CX_SPLIT_CU + gt(32, 0, 0)]);
+    if (whole) commit_cu(b, cx_off, cx_s4, r, lev, 32, 0, 0);
+    else
+        for (int a = 0; a < 4; a++) {
+            const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
+            const int sz = r.msz[(1 + y16 / 4) * 9 + 1 + x16 / 4];
+            b.put_bin(cs.tb, sz != 16, cx[CX_SPLIT_CU + gt(16, y16, x16)]);
+            const int ncu = sz == 16 ? 1 : 4;
+            for (int c = 0; c < ncu; c++) {
+                if (sz == 16) commit_cu(b, cx_off, cx_s4, r, lev, 16, y16, x16);
+                else commit_cu(b, cx_off, cx_s4, r, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
+            }
         }
+    b.put_terminate(r.last);   // HEVCe.c:1630
+    if (r.last) b.finish();    // HEVCe.c:1640
+    int err = 0;
+    if (!coder_equal(b.c, r.end)) err |= ERR_COMMIT_MISMATCH;   // the adopted trial state must be what the bytes produce
+    if (!r.last) {
+        const u32* nx = (const u32*)job.recs[ctu + 1].ctx;
+        for (int k = 0; k < CTXW - 1; k++) if (cw[k * NT] != nx[k]) err |= ERR_COMMIT_MISMATCH;
     }
+    if (b.c.n > b.cap) err |= ERR_OVERFLOW;
+    if (err) HEVCE_ATOMIC_OR(job.result + 1, err);
 }
 
 // stream header (HEVCe.c:665-691): constant NAL units with ue(width), ue(height) spliced into the SPS
@@ -1380,8 +1436,9 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
     }
     PHASE_END_T(P_MISC);
 
+    int ctu_idx = 0;
     for (int cy = 0; cy < H; cy += CTU) {
-        for (int cx = 0; cx < W; cx += CTU) {
+        for (int cx = 0; cx < W; cx += CTU, ctu_idx++) {
             const Avail av = {cx > 0, 0, cy > 0, cy > 0 && cx + CTU < W};   // HEVCe.c:1606-1609
             // ---- load: original (edge-replicated), neighbour samples, neighbour maps
             PAR_FOR(i, CTU * CTU) {
@@ -1396,8 +1453,9 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
                 sm.msz[(i + 1) * 9] = cx > 0 ? sm.msz[(i + 1) * 9 + 8] : (u8)CTU;      // left column = previous CTU's last column
                 sm.mpm[(i + 1) * 9] = cx > 0 ? sm.mpm[(i + 1) * 9 + 8] : (u8)1;
             }
-            PAR_FOR(i, CTXW) ((u32*)sm.start_ctx)[i] = ((const u32*)sm.live_ctx)[i];
-            PAR_FOR(one, 1) { sm.live.n = 0; sm.start = sm.live; }
+            CtuRec& rec = job.recs[ctu_idx];
+            PAR_FOR(i, CTXW) ((u32*)rec.ctx)[i] = ((const u32*)sm.live_ctx)[i];
+            PAR_FOR(one, 1) { sm.live.n = 0; rec.start = sm.live; sm.ctu_lev = job.levs + (size_t)ctu_idx * (CTU * CTU); }
             PHASE_END_T(P_LOAD);
 
             // ---- CU quadtree, z-order, children before the parent's own candidates (HEVCe.c:1403-1413)
@@ -1418,23 +1476,17 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
             // ---- store reconstruction + map row, terminate bin, commit the CTU's bytes
             PAR_FOR(i, CTU * CTU) job.rcon[(size_t)(cy + i / CTU) * W + cx + i % CTU] = HEVCE_WIN(sm, i / CTU, i % CTU);
             PAR_FOR(i, 8) sc.msz_line[cx / 4 + i] = sm.msz[8 * 9 + 1 + i];
+            PAR_FOR(i, 81) { rec.msz[i] = sm.msz[i]; rec.mpm[i] = sm.mpm[i]; }
+            PAR_FOR(i, 16) rec.kind[i] = sm.kind[i];
             PAR_FOR(one, 1) {
                 const int last = cy + CTU >= H && cx + CTU >= W;
                 Bac t = make_bac(sm.live);
                 t.put_terminate(last);                                                  // HEVCe.c:1630
                 if (last) t.finish();                                                   // HEVCe.c:1640
-                BacCommit b;
-                b.c = sm.start;
-                b.out = job.out + sm.stream_pos;
-                b.cap = imax(0, job.out_cap - sm.stream_pos);
-                const Cx cxs = {sm.start_ctx, 4};
-                commit_ctu(b, cxs, sm, sc.ctu_lev);
-                b.put_terminate(last);
-                if (last) b.finish();
-                if (!coder_equal(b.c, t.c)) sm.error |= ERR_COMMIT_MISMATCH;
-                for (int i = 0; i < NCTX; i++) if (sm.start_ctx[i] != sm.live_ctx[i]) sm.error |= ERR_COMMIT_MISMATCH;
-                if (b.c.n > b.cap) sm.error |= ERR_OVERFLOW;
-                sm.stream_pos += b.c.n;
+                rec.end = t.c;
+                rec.out_pos = sm.stream_pos;
+                rec.last = last;
+                sm.stream_pos += t.c.n;                                                 // bytes the commit pass will write
                 sm.live = t.c;
             }
             PHASE_END_T(P_COMMIT);
@@ -1442,7 +1494,7 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
     }
     PAR_FOR(one, 1) {
         job.result[0] = sm.stream_pos;
-        job.result[1] = sm.error;
+        if (sm.error) HEVCE_ATOMIC_OR(job.result + 1, sm.error);
     }
     PHASE_END_T(P_MISC);
 }

@@ -61,6 +61,16 @@ hevce_encode_kernel(const Job* __restrict__ jobs, const int* __restrict__ gangs,
     }
 }
 
+// Commit pass: one thread per CTU re-encodes the decided CTU with the byte-writing coder.  blockIdx.y = picture.
+__global__ void __launch_bounds__(NT) hevce_commit_kernel(const Job* __restrict__ jobs) {
+    CommitShared& cs = my_csm();
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += NT) ((u32*)&cs.tb)[i] = ((const u32*)&g_tables)[i];
+    __syncthreads();
+    const Job job = jobs[blockIdx.y];
+    const int nctu = (job.H / CTU) * (job.W / CTU), ctu = blockIdx.x * NT + threadIdx.x;
+    if (ctu < nctu) commit_ctu(job, ctu, threadIdx.x);
+}
+
 // integer-issue micro-benchmark: 8 independent IMAD chains + 8 independent LOP3/IADD3 chains per thread
 __global__ void __launch_bounds__(256) hevce_int_peak_kernel(int iters, int seed, int* sink) {
     int a[8], b[8];
@@ -132,10 +142,11 @@ int grow(T** p, size_t* cap, size_t need) {   // grow-only device buffer
 
 struct hevce_session {
     int device = 0, n = 0, grid = 0, launches = 0, ngangs = 0;
-    float kernel_ms = 0.f;
+    float kernel_ms = 0.f, commit_ms = 0.f;
+    int max_nctu = 0;
     long long h2d = 0, d2h = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     std::vector<Job> jobs;
     std::vector<size_t> img_off, rcon_off, out_off;
     std::vector<int> order, results;
@@ -150,6 +161,8 @@ struct hevce_session {
     Scratch* d_slots = nullptr; size_t c_slots = 0;
     s16 *d_glev = nullptr, *d_lev = nullptr; u8 *d_grec = nullptr, *d_line = nullptr;
     size_t c_glev = 0, c_lev = 0, c_grec = 0, c_line = 0;
+    CtuRec* d_recs = nullptr; size_t c_recs = 0;
+    std::vector<size_t> ctu_off;
     int line_pitch = 0;
     // pinned staging
     u8* h_stage = nullptr; size_t c_stage = 0;
@@ -172,7 +185,9 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     const int max_dim = hevce_internal_max_dim();
     s->n = n;
     s->jobs.assign(n, Job());
-    s->img_off.assign(n, 0); s->rcon_off.assign(n, 0); s->out_off.assign(n, 0);
+    s->img_off.assign(n, 0); s->rcon_off.assign(n, 0); s->out_off.assign(n, 0); s->ctu_off.assign(n, 0);
+    size_t co = 0;
+    s->max_nctu = 0;
     size_t io = 0, ro = 0, oo = 0;
     int maxW = CTU;
     for (int i = 0; i < n; i++) {
@@ -183,7 +198,9 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
         j.W = (std::min(xsz[i], max_dim) + CTU - 1) / CTU * CTU;
         j.q = qpd6[i];
         j.out_cap = 256 + 2 * j.H * j.W;
-        s->img_off[i] = io; s->rcon_off[i] = ro; s->out_off[i] = oo;
+        s->img_off[i] = io; s->rcon_off[i] = ro; s->out_off[i] = oo; s->ctu_off[i] = co;
+        co += (size_t)(j.H / CTU) * (j.W / CTU);
+        s->max_nctu = std::max(s->max_nctu, (j.H / CTU) * (j.W / CTU));
         // only the rows/columns the encoder can touch are transferred (a picture larger than the clamp is cropped)
         io += ((size_t)std::min(j.src_h, j.H) * j.src_w + 255) & ~(size_t)255;
         ro += (size_t)j.H * j.W;
@@ -224,14 +241,14 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     s->line_pitch = maxW / 4 + 32;
     if ((rc = grow(&s->d_glev, &s->c_glev, g * nlev))) return rc;
     if ((rc = grow(&s->d_grec, &s->c_grec, g * nrec))) return rc;
-    if ((rc = grow(&s->d_lev, &s->c_lev, g * CTU * CTU))) return rc;
+    if ((rc = grow(&s->d_lev, &s->c_lev, co * CTU * CTU))) return rc;
+    if ((rc = grow(&s->d_recs, &s->c_recs, co))) return rc;
     if ((rc = grow(&s->d_line, &s->c_line, g * (size_t)s->line_pitch))) return rc;
     if ((rc = grow(&s->d_slots, &s->c_slots, g))) return rc;
     std::vector<Scratch> slots(g);
     for (size_t k = 0; k < g; k++) {
         slots[k].glev = s->d_glev + k * nlev;
         slots[k].grec = s->d_grec + k * nrec;
-        slots[k].ctu_lev = s->d_lev + k * CTU * CTU;
         slots[k].msz_line = s->d_line + k * (size_t)s->line_pitch;
     }
     for (int i = 0; i < n; i++) {
@@ -240,6 +257,8 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
         j.rcon = s->d_rcon + s->rcon_off[i];
         j.out = s->d_out + s->out_off[i];
         j.result = s->d_results + 2 * i;
+        j.recs = s->d_recs + s->ctu_off[i];
+        j.levs = s->d_lev + s->ctu_off[i] * CTU * CTU;
     }
     CK(cudaMemcpyAsync(s->d_slots, slots.data(), g * sizeof(Scratch), cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->d_jobs, s->jobs.data(), (size_t)n * sizeof(Job), cudaMemcpyHostToDevice, s->stream));
@@ -253,7 +272,7 @@ extern "C" hevce_session* hevce_session_create(int device, int n, const int* ysz
     hevce_session* s = new hevce_session;
     s->device = device;
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
-        cudaEventCreate(&s->ev1) != cudaSuccess) {
+        cudaEventCreate(&s->ev1) != cudaSuccess || cudaEventCreate(&s->ev2) != cudaSuccess) {
         fprintf(stderr, "libhevce_b200: cannot create stream/events on device %d\n", device);
         hevce_session_destroy(s);
         return nullptr;
@@ -284,13 +303,21 @@ extern "C" int hevce_session_encode(hevce_session* s) {
     CK(cudaSetDevice(s->device));
     if (s->n == 0) return 0;
     CK(cudaMemsetAsync(s->d_counter, 0, sizeof(int), s->stream));
+    CK(cudaMemsetAsync(s->d_results, 0, 2 * (size_t)s->n * sizeof(int), s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
     hevce_encode_kernel<<<s->grid, NT * GANG, GANG * sizeof(Shared), s->stream>>>(s->d_jobs, s->d_order, s->ngangs, s->d_slots, s->d_counter);
     CK(cudaGetLastError());
     CK(cudaEventRecord(s->ev1, s->stream));
+    {
+        const dim3 grid((unsigned)((s->max_nctu + NT - 1) / NT), (unsigned)s->n);
+        hevce_commit_kernel<<<grid, NT, sizeof(CommitShared), s->stream>>>(s->d_jobs);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(s->ev2, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     CK(cudaEventElapsedTime(&s->kernel_ms, s->ev0, s->ev1));
-    s->launches++;
+    CK(cudaEventElapsedTime(&s->commit_ms, s->ev1, s->ev2));
+    s->launches += 2;
     return 0;
 }
 
@@ -336,6 +363,7 @@ extern "C" int hevce_session_download(hevce_session* s, unsigned char* const* pb
 }
 
 extern "C" float hevce_session_kernel_ms(const hevce_session* s) { return s ? s->kernel_ms : 0.f; }
+extern "C" float hevce_session_commit_ms(const hevce_session* s) { return s ? s->commit_ms : 0.f; }
 extern "C" int hevce_session_launches(const hevce_session* s) { return s ? s->launches : 0; }
 extern "C" int hevce_session_grid(const hevce_session* s) { return s ? s->grid : 0; }
 extern "C" long long hevce_session_h2d_bytes(const hevce_session* s) { return s ? s->h2d : 0; }
@@ -351,10 +379,11 @@ extern "C" void hevce_session_destroy(hevce_session* s) {
     cudaSetDevice(s->device);
     cudaFree(s->d_img); cudaFree(s->d_rcon); cudaFree(s->d_out); cudaFree(s->d_jobs); cudaFree(s->d_order);
     cudaFree(s->d_results); cudaFree(s->d_counter); cudaFree(s->d_slots); cudaFree(s->d_glev); cudaFree(s->d_grec);
-    cudaFree(s->d_lev); cudaFree(s->d_line);
+    cudaFree(s->d_lev); cudaFree(s->d_line); cudaFree(s->d_recs);
     if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev2) cudaEventDestroy(s->ev2);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }

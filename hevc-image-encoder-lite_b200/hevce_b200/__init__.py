@@ -22,7 +22,7 @@ _ip = ctypes.POINTER(ctypes.c_int)
 EXPORTS = [
     "HEVCImageEncoder", "HEVCImageEncoderBatch", "hevce_set_devices", "hevce_set_max_dim", "hevce_version",
     "hevce_measure_int_peak", "hevce_session_create", "hevce_session_upload", "hevce_session_encode",
-    "hevce_session_download", "hevce_session_kernel_ms", "hevce_session_launches", "hevce_session_grid",
+    "hevce_session_download", "hevce_session_kernel_ms", "hevce_session_commit_ms", "hevce_session_launches", "hevce_session_grid",
     "hevce_session_h2d_bytes", "hevce_session_d2h_bytes", "hevce_session_destroy",
 ]
 
@@ -64,8 +64,9 @@ def lib():
         L.hevce_session_encode.argtypes = [ctypes.c_void_p]
         L.hevce_session_download.restype = ctypes.c_int
         L.hevce_session_download.argtypes = [ctypes.c_void_p, ctypes.POINTER(_u8p), ctypes.POINTER(_u8p), _ip]
-        L.hevce_session_kernel_ms.restype = ctypes.c_float
-        L.hevce_session_kernel_ms.argtypes = [ctypes.c_void_p]
+        for f in ("hevce_session_kernel_ms", "hevce_session_commit_ms"):
+            getattr(L, f).restype = ctypes.c_float
+            getattr(L, f).argtypes = [ctypes.c_void_p]
         for f in ("hevce_session_launches", "hevce_session_grid"):
             getattr(L, f).restype = ctypes.c_int
             getattr(L, f).argtypes = [ctypes.c_void_p]
@@ -167,6 +168,10 @@ class Session:
         if rc < 0:
             raise HevceError(rc, "hevce_session_encode")
         return lib().hevce_session_kernel_ms(self._h)
+
+    @property
+    def commit_ms(self):
+        return lib().hevce_session_commit_ms(self._h)
 
     def download(self):
         outs, rcons = _out_buffers(self.shapes, self.max_dim)

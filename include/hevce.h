@@ -67,10 +67,11 @@ HEVCE_API int hevce_set_max_dim(int max_dim);
 typedef struct hevce_session hevce_session;
 HEVCE_API hevce_session *hevce_session_create(int device, int n, const int *ysz, const int *xsz, const int *qpd6);
 HEVCE_API int  hevce_session_upload(hevce_session *s, const unsigned char *const *imgs);      /* host -> HBM (pinned staging) */
-HEVCE_API int  hevce_session_encode(hevce_session *s);                                        /* one kernel launch, synchronous */
+HEVCE_API int  hevce_session_encode(hevce_session *s);                                        /* decision + commit kernels, synchronous */
 HEVCE_API int  hevce_session_download(hevce_session *s, unsigned char *const *pbuffers, unsigned char *const *img_rcons,
                             int *stream_len);                                       /* HBM -> host */
-HEVCE_API float hevce_session_kernel_ms(const hevce_session *s);   /* CUDA-event duration of the last encode launch */
+HEVCE_API float hevce_session_kernel_ms(const hevce_session *s);   /* CUDA-event duration of the last hevce_encode_kernel launch */
+HEVCE_API float hevce_session_commit_ms(const hevce_session *s);   /* ... of the hevce_commit_kernel launch that follows it */
 HEVCE_API int  hevce_session_launches(const hevce_session *s);     /* kernel launches issued so far by this session */
 HEVCE_API int  hevce_session_grid(const hevce_session *s);         /* CTAs of the persistent encode grid */
 HEVCE_API long long hevce_session_h2d_bytes(const hevce_session *s);

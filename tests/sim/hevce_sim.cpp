@@ -8,7 +8,7 @@
 
 #include "hevce_core.h"
 
-namespace hevce { int g_sim_order = 0; Shared* g_sim_sm = nullptr; }
+namespace hevce { int g_sim_order = 0; Shared* g_sim_sm = nullptr; CommitShared* g_sim_csm = nullptr; }
 
 extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned char* img, unsigned char* rcon,
                                 int* ysz, int* xsz, int q, int order, int max_dim, int* err) {
@@ -23,15 +23,25 @@ extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned 
     job.H = (imin(*ysz, max_dim) + CTU - 1) / CTU * CTU;
     job.W = (imin(*xsz, max_dim) + CTU - 1) / CTU * CTU;
     job.q = q; job.out_cap = out_cap;
-    std::vector<s16> glev((size_t)NCAND * LEV_STRIDE + 16), lev(CTU * CTU);
+    const int nctu = (job.H / CTU) * (job.W / CTU);
+    std::vector<s16> glev((size_t)NCAND * LEV_STRIDE + 16), lev((size_t)nctu * CTU * CTU);
+    std::vector<CtuRec> recs(nctu);
+    job.recs = recs.data(); job.levs = lev.data();
     std::vector<u8> grec((size_t)NREC * CTU * CTU), line(job.W / 4 + 8);
     Scratch sc;
-    sc.glev = glev.data(); sc.grec = grec.data(); sc.ctu_lev = lev.data(); sc.msz_line = line.data();
+    sc.glev = glev.data(); sc.grec = grec.data(); sc.msz_line = line.data();
     Shared* sm = new Shared;
     memset(sm, 0xA5, sizeof(Shared));   // shared memory is not zeroed on the GPU either
     g_sim_sm = sm;
     encode_picture(job, tables, *sm, sc);
     delete sm;
+    // commit pass (hevce_commit_kernel on the GPU): one CTU at a time here
+    CommitShared* cs = new CommitShared;
+    memset(cs, 0x5A, sizeof(CommitShared));
+    cs->tb = tables;
+    g_sim_csm = cs;
+    for (int c = 0; c < nctu; c++) commit_ctu(job, order == 1 ? nctu - 1 - c : c, (c * 7) % NT);
+    delete cs;
     *ysz = job.H; *xsz = job.W;
     if (err) *err = result[1];
     return result[0];
