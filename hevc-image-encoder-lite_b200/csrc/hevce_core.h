@@ -44,7 +44,8 @@ typedef uint32_t u32;
 // ------------------------------------------------------------------------------------------------------------
 constexpr int CTU = 32;
 constexpr int NT = 128;            // threads per picture
-constexpr int GANG = 4;            // pictures per CTA (lock-step groups of NT threads)
+constexpr int GANG = 6;            // pictures per CTA (lock-step groups of NT threads)
+constexpr int NLANE = 70;          // trial-coder lanes with a private context set (the 35 NxN-PU lanes reuse 0..34)
 constexpr int NCAND = 105;         // trial-coder lanes of a CU node: 35 one-TU + 35 four-TU + 35 NxN-PU candidates
 constexpr int NMODE = 35;
 constexpr int NCTX = 142;          // context bytes, same offsets as the reference struct (HEVCe.c:745-759)
@@ -278,7 +279,7 @@ struct BacT {
 typedef BacT<false> Bac;        // trial coder: full integer state, no byte store
 typedef BacT<true> BacCommit;   // commit coder: writes the CTU's bytes
 
-// context set: byte k at base[(k>>2)*s4 + (k&3)].  s4 = 4: plain array; s4 = 4*NCAND: lane-private column of the
+// context set: byte k at base[(k>>2)*s4 + (k&3)].  s4 = 4: plain array; s4 = 4*NLANE: lane-private column of the
 // word-interleaved shared-memory array (every lane owns one bank).  The base pointer is always derived from the
 // picture's shared-memory block inside the function that uses it, so the accesses stay LDS/STS.
 struct Cx {
@@ -363,13 +364,12 @@ struct Scratch {       // per picture slot, global memory (L2-resident working s
     u8* msz_line;      // CU-size map row of the CTU row above, W/4 entries
 };
 
-constexpr int POOL_BYTES = 29440;
-constexpr int AUX_CODER = 23552;        // pool tail: trial-coder results (free whenever they are used)
+constexpr int POOL_BYTES = 18624;
+constexpr int AUX_CODER = 16640;        // pool tail: trial-coder results (free whenever they are used)
 
 struct Shared {
-    Tables tb;
     alignas(16) u8 pool[POOL_BYTES];    // per-node carve-up: work blocks, predictions, borders (see Plan<S>)
-    u32 lane_ctx[CTXW * NCAND];         // lane-private context sets, word-interleaved
+    u32 lane_ctx[CTXW * NLANE];         // lane-private context sets, word-interleaved
     alignas(16) u8 ctx0[144];           // freshly initialised contexts for this picture's qpd6
     alignas(16) u8 live_ctx[144];
     alignas(16) u8 snap_ctx[3][144];
@@ -397,14 +397,19 @@ HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CO
 
 // The picture's shared-memory block.  Non-inlined functions fetch it through this accessor instead of taking a
 // reference parameter: the compiler then knows the address space and emits LDS/STS instead of generic loads.
+// The constant tables exist once per CTA, behind the GANG picture blocks.
 #if defined(__CUDA_ARCH__)
 extern __shared__ __align__(16) unsigned char hevce_smem[];
 __device__ __forceinline__ Shared& my_sm() { return reinterpret_cast<Shared*>(hevce_smem)[threadIdx.x / NT]; }
+__device__ __forceinline__ Tables& my_tb() { return *reinterpret_cast<Tables*>(hevce_smem + GANG * sizeof(Shared)); }
 #elif defined(__CUDACC__)
 inline Shared& my_sm() { return *static_cast<Shared*>(nullptr); }   // host pass of nvcc: declared, never executed
+inline Tables& my_tb() { return *static_cast<Tables*>(nullptr); }
 #else
 extern Shared* g_sim_sm;                                             // CTA simulator (tests/sim)
+extern Tables* g_sim_tb;
 inline Shared& my_sm() { return *g_sim_sm; }
+inline Tables& my_tb() { return *g_sim_tb; }
 #endif
 static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail too small");
 
@@ -657,7 +662,7 @@ extern CommitShared* g_sim_csm;
 inline CommitShared& my_csm() { return *g_sim_csm; }
 #endif
 struct MainEnv {
-    HEVCE_HD static const Tables& tables() { return my_sm().tb; }
+    HEVCE_HD static const Tables& tables() { return my_tb(); }
     HEVCE_HD static u8* base() { return (u8*)&my_sm(); }
 };
 struct CommitEnv {
@@ -763,7 +768,8 @@ struct Grp {
     int pred;           // u8  [n][T*T]
     int psum;           // int [n][T*T/4]   per (row, group column) sums for the group zero-out
     int bord;           // u8  shared: [2][4T+4] (unfiltered, filtered); private: [n][4T+4]
-    int rec;            // u8  [n][rec_stride] candidate-private reconstruction, pitch rec_pitch; -1: none
+    int rec;            // u8  priv: [n][4*T] edges of the candidate's own sub-TUs (bottom rows of TU 0,1; right columns of TU 0,2);
+                        //     NxN PU group: [n][16] the PU's reconstruction; -1: none
     int rec_stride, rec_pitch;
 };
 
@@ -783,9 +789,13 @@ HEVCE_HD inline void border_item(Shared& sm, const Grp& g, int item) {
     const int cand = g.priv ? which : 0;
     auto nb = [&](int y, int x) -> int {
         const int yy = g.ty + y, xx = g.tx + x;
-        if (g.priv) {
+        if (g.priv) {   // inside the CU only the sub-TU edges can be asked for: row H-1 (bottom of TU 0/1) or column H-1 (right of TU 0/2)
             const int cy = yy - g.cuy, cx = xx - g.cux;
-            if (cy >= 0 && cx >= 0 && cy < g.cus && cx < g.cus) return sm.pool[g.rec + cand * g.rec_stride + cy * g.rec_pitch + cx];
+            if (cy >= 0 && cx >= 0 && cy < g.cus && cx < g.cus) {
+                const u8* e = sm.pool + g.rec + cand * (4 * T);
+                if (cy == T - 1) return e[(cx >= T ? T : 0) + (cx & (T - 1))];
+                return e[2 * T + (cy >= T ? T : 0) + (cy & (T - 1))];
+            }
         }
         return HEVCE_WIN(sm, yy, xx);
     };
@@ -934,7 +944,7 @@ HEVCE_HD inline void phase_c_item(Shared& sm, const Scratch& sc, const Grp& g, i
     const int c = item >> LG, x = item & (T - 1), gx = x >> 2, ci = g.cand0 + c;
     s16* bp = (s16*)(sm.pool + g.blk) + c * BLK + x;
     const int* ps = (const int*)(sm.pool + g.psum) + c * (T * T / 4) + gx;
-    const u8* inv = sm.tb.inv4[scan_type(T, g.mode0 + c)] + (x & 3);
+    const u8* inv = my_tb().inv4[scan_type(T, g.mode0 + c)] + (x & 3);
     s16* lp = sc.glev + (size_t)ci * LEV_STRIDE + g.tu * (T * T) + gx * 16;
     const int sh = 21 - LG + q, thr = 9 << sh >> 2, qs = 7 - LG + q;
     int v[T], o[T];
@@ -992,7 +1002,9 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
         for (int x = 0; x < T; x++) o[x] = 0;
     }
     const int ry = g.ty - g.cuy + y, rx = g.tx - g.cux;
-    u8* rs = g.rec >= 0 ? sm.pool + g.rec + c * g.rec_stride + ry * g.rec_pitch + rx : nullptr;
+    u8* rs = (g.rec >= 0 && !g.priv) ? sm.pool + g.rec + c * g.rec_stride + ry * g.rec_pitch + rx : nullptr;
+    u8* er = nullptr;   // four-TU candidates keep the edges later sub-TUs predict from: bottom row of TU 0/1
+    if (g.priv && g.tu < 2 && y == T - 1) er = sm.pool + g.rec + c * (4 * T) + g.tu * T;
     u8* rg = g.grec ? sc.grec + (size_t)ci * (CTU * CTU) + ry * g.cus + rx : nullptr;
     int sse = 0;
 #pragma unroll
@@ -1002,7 +1014,9 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
         const int d = (int)org[x] - rec;
         sse += d * d;
         if (rs) rs[x] = (u8)rec;
+        if (er) er[x] = (u8)rec;
         if (rg) rg[x] = (u8)rec;
+        if (x == T - 1 && g.priv && !(g.tu & 1)) sm.pool[g.rec + c * (4 * T) + 2 * T + (g.tu >> 1) * T + y] = (u8)rec;   // right column of TU 0/2
     }
     HEVCE_ATOMIC_ADD(&sm.cand_sse[ci], sse);
 }
@@ -1048,9 +1062,9 @@ HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, 
 // candidates (T = S/2), group 2 (S = 8 only) = NxN PU candidates (T = 4)
 template <int S> struct Plan {
     static constexpr int H = S / 2;
-    static constexpr int N0 = S == 8 ? 35 : S == 16 ? 9 : 2;     // one-TU candidates per round
+    static constexpr int N0 = S == 8 ? 35 : S == 16 ? 6 : 2;     // one-TU candidates per round
     static constexpr int N1 = S == 32 ? 7 : 35;                  // four-TU candidates per chunk
-    static constexpr int ROUNDS = S == 32 ? 20 : 4;              // 32: 5 chunks of 7 modes x 4 sub-TUs
+    static constexpr int ROUNDS = S == 32 ? 20 : S == 16 ? 6 : 4; // 32: 5 chunks of 7 modes x 4 sub-TUs; 16: 4 sub-TU rounds + 2 one-TU-only
     static constexpr int al(int v) { return (v + 15) & ~15; }
     // group 0
     static constexpr int BLK0 = 0;
@@ -1064,7 +1078,7 @@ template <int S> struct Plan {
     static constexpr int PSUM1 = PRED1 + al(N1 * H * H);
     static constexpr int BORD1 = PSUM1 + al(N1 * H * H);
     static constexpr int REC1 = BORD1 + al(N1 * Dim<H>::BS);
-    static constexpr int END1 = REC1 + al(N1 * S * S);
+    static constexpr int END1 = REC1 + al(N1 * 4 * H);           // sub-TU edges only
     // group 2 (S == 8)
     static constexpr int BLK2 = END1;
     static constexpr int PRED2 = BLK2 + al(35 * Dim<4>::BLK * 2);
@@ -1090,15 +1104,16 @@ template <int S>
 HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int cand, int depth, int split_ctx, int pmL, int pmA) {
     constexpr int H = S / 2;
     const bool pu = cand >= 2 * NMODE;
+    const int slot = pu ? cand - 2 * NMODE : cand;   // context-set lane
     const int step = cand / NMODE, mode = cand - step * NMODE;
     Bac b = make_bac(sm.snap[depth]);
     if (pu) coder_reset(b.c);
     const int base_len = pu ? coder_len(b.c) : coder_len(sm.snap[depth]);
     {
         const u32* src = (const u32*)(pu ? sm.ctx0 : sm.snap_ctx[depth]);
-        u32* dst = sm.lane_ctx + cand;
+        u32* dst = sm.lane_ctx + slot;
 #pragma unroll 4
-        for (int k = 0; k < CTXW; k++) dst[k * NCAND] = src[k];
+        for (int k = 0; k < CTXW; k++) dst[k * NLANE] = src[k];
     }
     CuDesc d;
     d.s = S; d.kind = pu ? 3 : step; d.split_ctx = split_ctx;
@@ -1110,7 +1125,7 @@ HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int cand, int dep
     } else {
         d.lev[0] = lev; d.mlo[0] = sm.cgnz[cand][0]; d.mhi = pu ? 0u : sm.cgnz[cand][1];
     }
-    code_cu<Bac, MainEnv>(b, sm_off(sm, sm.lane_ctx + cand), 4 * NCAND, d);
+    code_cu<Bac, MainEnv>(b, sm_off(sm, sm.lane_ctx + slot), 4 * NLANE, d);
     sm.cand_bits[cand] = coder_len(b.c) - base_len;
     if (!pu) cand_coder(sm)[cand] = b.c;
 }
@@ -1150,11 +1165,11 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             g0.rec = -1; g0.rec_stride = 0; g0.rec_pitch = 0;
         }
         {   // four-TU candidates: sub-TU k of a chunk of modes, each with its own reconstruction as neighbour
-            const int m0 = chunk * P::N1, n = imax(0, imin(P::N1, NMODE - m0));
+            const int m0 = chunk * P::N1, n = (S == 16 && r >= 4) ? 0 : imax(0, imin(P::N1, NMODE - m0));
             g1.n = n; g1.cand0 = NMODE + m0; g1.mode0 = m0; g1.ty = y0 + (k >> 1) * H; g1.tx = x0 + (k & 1) * H; g1.av = sub_avail(av, k); g1.priv = 1;
             g1.cuy = y0; g1.cux = x0; g1.cus = S; g1.tu = k; g1.one_tu = 0; g1.grec = 1;
             g1.blk = P::BLK1; g1.pred = P::PRED1; g1.psum = P::PSUM1; g1.bord = P::BORD1;
-            g1.rec = P::REC1; g1.rec_stride = S * S; g1.rec_pitch = S;
+            g1.rec = P::REC1; g1.rec_stride = 4 * H; g1.rec_pitch = 0;
         }
         g2.n = 0;
         if (S == 8) {   // NxN PU k: all 35 modes, neighbours from the window (earlier PUs' winners are already there)
@@ -1171,22 +1186,22 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         PHASE_END_T(P_BORDER);
         // ---- phase A
         if (g0.n) run_phase_a<S>(g0, 0);
-        run_phase_a<H>(g1, i0);
+        if (g1.n) run_phase_a<H>(g1, i0);
         if (S == 8) run_phase_a<4>(g2, i0 + i1);
         PHASE_END_T(P_A);
         // ---- phase B
         if (g0.n) run_phase_b<S>(g0, 0, q);
-        run_phase_b<H>(g1, i0, q);
+        if (g1.n) run_phase_b<H>(g1, i0, q);
         if (S == 8) run_phase_b<4>(g2, i0 + i1, q);
         PHASE_END_T(P_B);
         // ---- phase C
         if (g0.n) run_phase_c<S>(sc, g0, 0, q);
-        run_phase_c<H>(sc, g1, i0, q);
+        if (g1.n) run_phase_c<H>(sc, g1, i0, q);
         if (S == 8) run_phase_c<4>(sc, g2, i0 + i1, q);
         PHASE_END_T(P_C);
         // ---- phase D (+ the trial coders that only need the levels of phase C)
         if (g0.n) run_phase_d<S>(sc, g0, 0);
-        run_phase_d<H>(sc, g1, i0);
+        if (g1.n) run_phase_d<H>(sc, g1, i0);
         if (S == 8) {
             run_phase_d<4>(sc, g2, i0 + i1);
             PAR_FOR(t, NT) {
@@ -1279,7 +1294,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             HEVCE_WIN(sm, y0 + i / S, x0 + i % S) = rp[i];
             clev[i] = lp[i];
         }
-        PAR_FOR(i, CTXW) ((u32*)sm.live_ctx)[i] = sm.lane_ctx[i * NCAND + win];
+        PAR_FOR(i, CTXW) ((u32*)sm.live_ctx)[i] = sm.lane_ctx[i * NLANE + win];
         PAR_FOR(i, N4 * N4) {
             const int idx = (my + i / N4) * 9 + mx + i % N4;
             sm.msz[idx] = (u8)S;
@@ -1305,7 +1320,7 @@ HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
             const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
             Bac b = make_bac(sm.live);
             const Cx cx = {sm.live_ctx, 4};
-            b.put_bin(sm.tb, 1, cx[CX_SPLIT_CU + (S > sm.msz[my * 9 + mx - 1]) + (S > sm.msz[(my - 1) * 9 + mx])]);   // HEVCe.c:943-947
+            b.put_bin(my_tb(), 1, cx[CX_SPLIT_CU + (S > sm.msz[my * 9 + mx - 1]) + (S > sm.msz[(my - 1) * 9 + mx])]);   // HEVCe.c:943-947
             sm.live = b.c;
         }
         PHASE_END_T(P_ENTER);
@@ -1416,10 +1431,8 @@ HEVCE_HD inline int write_header(u8* out, int q, int H, int W) {
 // ------------------------------------------------------------------------------------------------------------
 HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared& sm, const Scratch& sc) {
     const int q = job.q, H = job.H, W = job.W;
-    PAR_FOR(i, (int)(sizeof(Tables) / 4)) ((u32*)&sm.tb)[i] = ((const u32*)&tables)[i];
-    PHASE_END_T(P_MISC);
     PAR_FOR(i, 144) {
-        const u8 v = i < NCTX ? ctx_init_value(sm.tb.ctx_iv[i], q) : (u8)0;
+        const u8 v = i < NCTX ? ctx_init_value(my_tb().ctx_iv[i], q) : (u8)0;
         sm.ctx0[i] = v;
         sm.live_ctx[i] = v;
     }

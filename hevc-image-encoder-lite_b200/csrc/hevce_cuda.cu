@@ -50,6 +50,7 @@ hevce_encode_kernel(const Job* __restrict__ jobs, const int* __restrict__ gangs,
     Shared& sm = my_sm();
     __shared__ int s_next;
     const Scratch sc = slots[blockIdx.x * GANG + member];
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += NT * GANG) ((u32*)&my_tb())[i] = ((const u32*)&g_tables)[i];
     for (;;) {
         if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
         __syncthreads();
@@ -117,8 +118,8 @@ int device_prepare(int device) {
     fill_tables(host_tables);
     CK(cudaMemcpyToSymbol(g_tables, &host_tables, sizeof(Tables)));
     int occ = 0;
-    CK(cudaFuncSetAttribute(hevce_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GANG * sizeof(Shared))));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevce_encode_kernel, NT * GANG, GANG * sizeof(Shared)));
+    CK(cudaFuncSetAttribute(hevce_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GANG * sizeof(Shared) + sizeof(Tables))));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevce_encode_kernel, NT * GANG, GANG * sizeof(Shared) + sizeof(Tables)));
     if (occ < 1) occ = 1;
     g_dev[device].sms = prop.multiProcessorCount;
     g_dev[device].ctas_per_sm = occ;
@@ -305,7 +306,7 @@ extern "C" int hevce_session_encode(hevce_session* s) {
     CK(cudaMemsetAsync(s->d_counter, 0, sizeof(int), s->stream));
     CK(cudaMemsetAsync(s->d_results, 0, 2 * (size_t)s->n * sizeof(int), s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
-    hevce_encode_kernel<<<s->grid, NT * GANG, GANG * sizeof(Shared), s->stream>>>(s->d_jobs, s->d_order, s->ngangs, s->d_slots, s->d_counter);
+    hevce_encode_kernel<<<s->grid, NT * GANG, GANG * sizeof(Shared) + sizeof(Tables), s->stream>>>(s->d_jobs, s->d_order, s->ngangs, s->d_slots, s->d_counter);
     CK(cudaGetLastError());
     CK(cudaEventRecord(s->ev1, s->stream));
     {

@@ -8,7 +8,7 @@
 
 #include "hevce_core.h"
 
-namespace hevce { int g_sim_order = 0; Shared* g_sim_sm = nullptr; CommitShared* g_sim_csm = nullptr; }
+namespace hevce { int g_sim_order = 0; Shared* g_sim_sm = nullptr; Tables* g_sim_tb = nullptr; CommitShared* g_sim_csm = nullptr; }
 
 extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned char* img, unsigned char* rcon,
                                 int* ysz, int* xsz, int q, int order, int max_dim, int* err) {
@@ -33,6 +33,7 @@ extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned 
     Shared* sm = new Shared;
     memset(sm, 0xA5, sizeof(Shared));   // shared memory is not zeroed on the GPU either
     g_sim_sm = sm;
+    g_sim_tb = &tables;
     encode_picture(job, tables, *sm, sc);
     delete sm;
     // commit pass (hevce_commit_kernel on the GPU): one CTU at a time here
