@@ -421,6 +421,7 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 #define HEVCE_TID ((int)(threadIdx.x & (NT - 1)))
 #define PAR_FOR(item, n) for (int item = HEVCE_TID; item < (n); item += NT)
 #define PAR_FOR_OFF(item, n, off) for (int item = (HEVCE_TID + NT - ((off) & (NT - 1))) & (NT - 1); item < (n); item += NT)
+#define PAR_FOR_SUB(item, n, nthr) for (int item = HEVCE_TID < (nthr) ? HEVCE_TID : (n); item < (n); item += (nthr))   // first nthr threads only
 #define PHASE_END() __syncthreads()
 #if defined(HEVCE_PROFILE)   // per-phase latency histogram (development builds only)
 extern __device__ unsigned long long g_phase_cycles[16];
@@ -444,6 +445,7 @@ inline int sim_item(int i, int n) {
 }
 #define PAR_FOR(item, n) for (int item##_i = 0, item = 0; item##_i < (n) && ((item = sim_item(item##_i, (n))), true); item##_i++)
 #define PAR_FOR_OFF(item, n, off) PAR_FOR(item, n)
+#define PAR_FOR_SUB(item, n, nthr) PAR_FOR(item, n)
 #define PHASE_END() ((void)0)
 #define PHASE_END_T(tag) ((void)0)
 #define HEVCE_ATOMIC_OR(p, v) (*(p) |= (v))
@@ -800,21 +802,22 @@ HEVCE_HD inline void border_item(Shared& sm, const Grp& g, int item) {
         return HEVCE_WIN(sm, yy, xx);
     };
     const Avail& a = g.av;
-    int cor;
-    if (a.L && a.A) cor = nb(-1, -1);
-    else if (a.L) cor = nb(0, -1);
-    else if (a.A) cor = nb(-1, 0);
-    else cor = 128;
+    auto cor = [&]() -> int {   // HEVCe.c:212-219; only evaluated for the corner itself or as a substitute
+        if (a.L && a.A) return nb(-1, -1);
+        if (a.L) return nb(0, -1);
+        if (a.A) return nb(-1, 0);
+        return 128;
+    };
     auto u = [&](int jj) -> int {
-        if (jj == 2 * T) return cor;
+        if (jj == 2 * T) return cor();
         if (jj < 2 * T) {
             const int i = 2 * T - 1 - jj;
-            if (i < T) return a.L ? nb(i, -1) : cor;
-            return a.LB ? nb(i, -1) : (a.L ? nb(T - 1, -1) : cor);
+            if (i < T ? a.L : a.LB) return nb(i, -1);
+            return a.L ? nb(T - 1, -1) : cor();
         }
         const int i = jj - 2 * T - 1;
-        if (i < T) return a.A ? nb(-1, i) : cor;
-        return a.AR ? nb(-1, i) : (a.A ? nb(-1, T - 1) : cor);
+        if (i < T ? a.A : a.AR) return nb(-1, i);
+        return a.A ? nb(-1, T - 1) : cor();
     };
     int v = u(j);
     const bool filt = g.priv ? use_filtered(T, g.mode0 + cand) != 0 : which == 1;
@@ -1051,11 +1054,12 @@ HEVCE_HD HEVCE_NOINLINE void run_phase_c(const Scratch& scref, const Grp& gref, 
     PAR_FOR_OFF(item, g.n * T, off) phase_c_item<T>(sm, sc, g, item, q);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, int off, int nthr) {
     Shared& sm = my_sm();
     const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
     const Scratch sc = scref;
-    PAR_FOR_OFF(item, g.n * T, off) phase_d_item<T>(sm, sc, g, item);
+    if (nthr < NT) { PAR_FOR_SUB(item, g.n * T, nthr) phase_d_item<T>(sm, sc, g, item); }   // the other threads run trial coders meanwhile
+    else { PAR_FOR_OFF(item, g.n * T, off) phase_d_item<T>(sm, sc, g, item); }
 }
 
 // shared-memory carve-up of the pool for a node of size S: group 0 = one-TU candidates (T = S), group 1 = four-TU
@@ -1109,8 +1113,14 @@ HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int cand, int dep
     Bac b = make_bac(sm.snap[depth]);
     if (pu) coder_reset(b.c);
     const int base_len = pu ? coder_len(b.c) : coder_len(sm.snap[depth]);
-    {
-        const u32* src = (const u32*)(pu ? sm.ctx0 : sm.snap_ctx[depth]);
+    if (pu) {   // a 4x4 luma TU touches last_x/y row 0 (words 4,5,10,11), sig 0..8 (17-19), greater1 0..15 (28-31), greater2 0..3 (34)
+        const u32* src = (const u32*)sm.ctx0;
+        u32* dst = sm.lane_ctx + slot;
+        const int W4[12] = {4, 5, 10, 11, 17, 18, 19, 28, 29, 30, 31, 34};
+#pragma unroll
+        for (int k = 0; k < 12; k++) dst[W4[k] * NLANE] = src[W4[k]];
+    } else {
+        const u32* src = (const u32*)sm.snap_ctx[depth];
         u32* dst = sm.lane_ctx + slot;
 #pragma unroll 4
         for (int k = 0; k < CTXW; k++) dst[k * NLANE] = src[k];
@@ -1200,15 +1210,15 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         if (S == 8) run_phase_c<4>(sc, g2, i0 + i1, q);
         PHASE_END_T(P_C);
         // ---- phase D (+ the trial coders that only need the levels of phase C)
-        if (g0.n) run_phase_d<S>(sc, g0, 0);
-        if (g1.n) run_phase_d<H>(sc, g1, i0);
+        constexpr int ND = S == 8 ? NT - NMODE : NT;   // 8x8 nodes: the last 35 threads code the NxN PU modes of this round
         if (S == 8) {
-            run_phase_d<4>(sc, g2, i0 + i1);
             PAR_FOR(t, NT) {
-                const int cand = lane_to_cand(NSTEP, t);
-                if (cand >= 2 * NMODE) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);   // NxN PU modes of this round
+                if (t >= ND) trial_lane<S>(sm, sc, 2 * NMODE + t - ND, depth, gtL + gtA, pmL, pmA);
             }
         }
+        if (g0.n) run_phase_d<S>(sc, g0, 0, ND);
+        if (g1.n) run_phase_d<H>(sc, g1, i0, ND);
+        if (S == 8) run_phase_d<4>(sc, g2, i0 + i1, ND);
         PHASE_END_T(P_D_TRIAL);
         if (S == 8) {
             PAR_FOR(one, 1) {   // best PU mode, last minimum wins (HEVCe.c:1521)
