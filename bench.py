@@ -240,7 +240,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": "configs[2] shard: synthetic 768x512 8-bit grayscale (Kodak-derived, tests/workloads.py), qpd6=2",
                    "images_per_gpu": n, "qpd6": a.qpd6, "pixels_per_step_per_gpu": pixels_step, "grid_ctas": grid,
-                   "l2": f"inputs larger than L2 ({n * KODAK_PIXELS / 1e6:.0f} MB of pictures + {n * 0.77:.0f} MB scratch per step)",
+                   "l2": f"inputs larger than L2: {n * KODAK_PIXELS / 1e6:.0f} MB of pictures + {n * 384 * 2.45e-3:.0f} MB of per-CTU records/levels written and re-read per step",
                    "parallelism": f"{world} x independent shards, no collective"},
         "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "HEVCImageEncoderBatch (host buffers, pinned staging inside the library)", "steps": e2e_steps},

@@ -76,7 +76,7 @@ HEVCE_HD inline int bitlen(unsigned v) {
 // constant tables (filled on the host by fill_tables(), copied to __constant__ and from there to shared memory)
 // ------------------------------------------------------------------------------------------------------------
 struct Tables {
-    u8 lps[64 * 4];        // rangeTabLps                                   (HEVCe.c:704-713)
+    u32 lps4[64];          // rangeTabLps, one word per state: byte q = LPS range for (range>>6)&3 == q  (HEVCe.c:704-713)
     u8 next_lps[128];      // (state<<1|mps) after an LPS                   (HEVCe.c:702)
     u8 ctx_iv[144];        // context init values by byte offset            (HEVCe.c:763-777)
     u8 scan4[3][16];       // in-CG scan, (y<<2)|x : diag / horizontal / vertical
@@ -115,8 +115,7 @@ inline void fill_tables(Tables& t) {
     static const u8 ABSV[6] = {138, 153, 136, 167, 152, 152};
     static const u8 P4[16] = {0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8};
     static const u8 GMIN[12] = {0, 1, 2, 3, 4, 6, 8, 12, 16, 24, 0, 0};
-    for (int s = 0; s < 64; s++)
-        for (int r = 0; r < 4; r++) t.lps[s * 4 + r] = LPS[s][r];
+    for (int s = 0; s < 64; s++) t.lps4[s] = (u32)LPS[s][0] | ((u32)LPS[s][1] << 8) | ((u32)LPS[s][2] << 16) | ((u32)LPS[s][3] << 24);
     for (int s = 0; s < 64; s++)
         for (int m = 0; m < 2; m++) t.next_lps[(s << 1) | m] = (u8)((TRANS_LPS[s] << 1) | (s == 0 ? !m : m));
     for (int i = 0; i < 144; i++) t.ctx_iv[i] = 154;
@@ -228,17 +227,32 @@ struct BacT {
         const int lead = c.low >> (24 - c.nbits);
         c.nbits += 8;
         c.low &= (int)(0xFFFFFFFFu >> c.nbits);
-        if (lead == 0xff) c.nbytes++;
-        else if (c.nbytes > 0) {
-            const int carry = lead >> 8;
-            emit(c.held + carry);
-            c.held = lead & 0xff;
-            for (; c.nbytes > 1; c.nbytes--) emit((0xff + carry) & 0xff);
-        } else { c.nbytes = 1; c.held = lead; }
+        if (EMIT) {
+            if (lead == 0xff) c.nbytes++;
+            else if (c.nbytes > 0) {
+                const int carry = lead >> 8;
+                emit(c.held + carry);
+                c.held = lead & 0xff;
+                for (; c.nbytes > 1; c.nbytes--) emit((0xff + carry) & 0xff);
+            } else { c.nbytes = 1; c.held = lead; }
+        } else {
+            // Trial coder: the same state machine with the common case (release the held byte) branch-free.  In a warp
+            // some lane takes this path on most bins, so its length is paid almost every time.
+            const int ff = lead == 0xff, had = c.nbytes > 0, rel = !ff & had, carry = lead >> 8;
+            const int b = (c.held + carry) & 0xff;
+            const int epb = rel & (c.z >= 2) & (b <= 3);
+            c.n += rel + epb;
+            c.z = rel ? (b ? 0 : (epb ? 1 : c.z + 1)) : c.z;
+            if (rel & (c.nbytes > 1)) {   // rare: a run of pending 0xFF bytes is released behind it
+                for (; c.nbytes > 1; c.nbytes--) emit((0xff + carry) & 0xff);
+            }
+            c.held = ff ? c.held : (had ? (lead & 0xff) : lead);
+            c.nbytes = ff ? c.nbytes + 1 : 1;
+        }
     }
     HEVCE_HD void put_bin(const Tables& tb, int bin, u8& cx) {   // HEVCe.c:914-933, both branches computed, then selected
         const int v = cx;
-        const int lps = tb.lps[(v >> 1) * 4 + ((c.range >> 6) & 3)];
+        const int lps = (int)((tb.lps4[v >> 1] >> (((c.range >> 6) & 3) * 8)) & 0xffu);   // the load depends on the context only, not on range
         const int nlps = tb.next_lps[v];
         const int rmps = c.range - lps;
         const bool is_lps = (bin != 0) != ((v & 1) != 0);

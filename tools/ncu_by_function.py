@@ -20,7 +20,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture
 ins, cur, inker = [], None, False
 for l in dis.splitlines():
     if l.startswith(".text."):
-        inker = "int_peak" not in l
+        inker = "hevce_encode_kernel" in l
         continue
     if not inker:
         continue
