@@ -33,6 +33,22 @@
 #define HEVCE_NOINLINE __attribute__((noinline))
 #endif
 
+// tuning switches: tools/ab_variants.py builds A/B variants of the library with -DHEVCE_OPT_xxx=0/1
+// measured on B200 (tools/ab_variants.py, 888 x 64x64, qpd6=2): LPS4=1 +1.5 %, FLUSH=1 +4 % kernel time -> both off;
+// BINSEL neutral; GANG 6 (80 regs) = GANG 5 (96 regs) > GANG 4 by 12 %.
+#ifndef HEVCE_OPT_LPS4
+#define HEVCE_OPT_LPS4 0
+#endif
+#ifndef HEVCE_OPT_FLUSH
+#define HEVCE_OPT_FLUSH 0
+#endif
+#ifndef HEVCE_OPT_BINSEL
+#define HEVCE_OPT_BINSEL 1
+#endif
+#ifndef HEVCE_OPT_GANG
+#define HEVCE_OPT_GANG 6
+#endif
+
 namespace hevce {
 
 typedef uint8_t u8;
@@ -44,7 +60,7 @@ typedef uint32_t u32;
 // ------------------------------------------------------------------------------------------------------------
 constexpr int CTU = 32;
 constexpr int NT = 128;            // threads per picture
-constexpr int GANG = 6;            // pictures per CTA (lock-step groups of NT threads)
+constexpr int GANG = HEVCE_OPT_GANG;            // pictures per CTA (lock-step groups of NT threads)
 constexpr int NLANE = 70;          // trial-coder lanes with a private context set (the 35 NxN-PU lanes reuse 0..34)
 constexpr int NCAND = 105;         // trial-coder lanes of a CU node: 35 one-TU + 35 four-TU + 35 NxN-PU candidates
 constexpr int NMODE = 35;
@@ -227,7 +243,7 @@ struct BacT {
         const int lead = c.low >> (24 - c.nbits);
         c.nbits += 8;
         c.low &= (int)(0xFFFFFFFFu >> c.nbits);
-        if (EMIT) {
+        if (EMIT || !HEVCE_OPT_FLUSH) {
             if (lead == 0xff) c.nbytes++;
             else if (c.nbytes > 0) {
                 const int carry = lead >> 8;
@@ -252,7 +268,12 @@ struct BacT {
     }
     HEVCE_HD void put_bin(const Tables& tb, int bin, u8& cx) {   // HEVCe.c:914-933, both branches computed, then selected
         const int v = cx;
+#if HEVCE_OPT_LPS4
         const int lps = (int)((tb.lps4[v >> 1] >> (((c.range >> 6) & 3) * 8)) & 0xffu);   // the load depends on the context only, not on range
+#else
+        const int lps = ((const u8*)tb.lps4)[(v >> 1) * 4 + ((c.range >> 6) & 3)];
+#endif
+#if HEVCE_OPT_BINSEL
         const int nlps = tb.next_lps[v];
         const int rmps = c.range - lps;
         const bool is_lps = (bin != 0) != ((v & 1) != 0);
@@ -262,6 +283,19 @@ struct BacT {
         c.range = (is_lps ? lps : rmps) << sh;
         c.nbits -= sh;
         cx = (u8)(is_lps ? nlps : (v < 124 ? v + 2 : v));           // HEVCe.c:701-702
+#else
+        c.range -= lps;
+        if ((bin != 0) != ((v & 1) != 0)) {
+            const int nb = lps < 8 ? 6 : 9 - bitlen((unsigned)lps);
+            cx = tb.next_lps[v];
+            c.low = (int)((unsigned)(c.low + c.range) << nb);
+            c.range = lps << nb;
+            c.nbits -= nb;
+        } else {
+            cx = (u8)(v < 124 ? v + 2 : v);
+            if (c.range < 256) { c.low = (int)((unsigned)c.low << 1); c.range <<= 1; c.nbits--; }
+        }
+#endif
         carry_out();
     }
     HEVCE_HD void put_bypass(int bins, int len) {   // HEVCe.c:899-911
