@@ -205,14 +205,15 @@ def main():
 
     # ---- end-to-end arm through the public C entry point with host buffers
     e2e_steps = a.steps
-    H.HEVCImageEncoderBatch(imgs[: min(n, 64)], a.qpd6)   # warm the pooled session
+    host_out = H.alloc_outputs(shapes)                     # caller-owned pbuffer / img_rcon arrays, reused like a C caller would
+    H.HEVCImageEncoderBatch(imgs, a.qpd6, outputs=host_out, copy_streams=False)   # warm-up: pooled session, pinned staging, page faults
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        s2, r2 = H.HEVCImageEncoderBatch(imgs, a.qpd6)
+        s2, r2 = H.HEVCImageEncoderBatch(imgs, a.qpd6, outputs=host_out, copy_streams=False)
     barrier()
     dt2 = max_over_ranks(time.perf_counter() - t0)
-    if hashlib.sha256(b"".join(hashlib.sha256(s).digest() for s in s2)).hexdigest() != digest:
+    if hashlib.sha256(b"".join(hashlib.sha256(bytes(s)).digest() for s in s2)).hexdigest() != digest:
         raise SystemExit("bench.py: e2e arm produced different streams than the device-resident arm")
     e2e_value = world * pixels_step * e2e_steps / dt2 / 1e6
     h2d = sum(i.size for i in imgs)

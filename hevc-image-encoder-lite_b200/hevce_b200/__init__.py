@@ -108,12 +108,19 @@ def HEVCImageEncoder(img, qpd6, max_dim=8192):
     return out[:n].tobytes(), rcon
 
 
-def HEVCImageEncoderBatch(imgs, qpd6, max_dim=8192):
-    """n pictures in one call (sharded over the selected GPUs). qpd6: int or sequence. Returns (streams, recons)."""
+def alloc_outputs(shapes, max_dim=8192):
+    """Caller-owned output buffers (stream, reconstruction) for pictures of the given shapes; reusable across calls,
+    exactly like the pbuffer / img_rcon arrays a C caller keeps."""
+    return _out_buffers(shapes, max_dim)
+
+
+def HEVCImageEncoderBatch(imgs, qpd6, max_dim=8192, outputs=None, copy_streams=True):
+    """n pictures in one call (sharded over the selected GPUs). qpd6: int or sequence. Returns (streams, recons).
+    outputs: buffers from alloc_outputs() to reuse; copy_streams=False returns views into them instead of bytes."""
     imgs = [np.ascontiguousarray(i, dtype=np.uint8) for i in imgs]
     n = len(imgs)
     qs = [int(qpd6)] * n if np.isscalar(qpd6) else [int(q) for q in qpd6]
-    outs, rcons = _out_buffers([i.shape for i in imgs], max_dim)
+    outs, rcons = outputs if outputs is not None else _out_buffers([i.shape for i in imgs], max_dim)
     ys = (ctypes.c_int * n)(*[i.shape[0] for i in imgs])
     xs = (ctypes.c_int * n)(*[i.shape[1] for i in imgs])
     qa = (ctypes.c_int * n)(*qs)
@@ -121,6 +128,8 @@ def HEVCImageEncoderBatch(imgs, qpd6, max_dim=8192):
     rc = lib().HEVCImageEncoderBatch(n, _ptr_array(outs), _ptr_array(imgs), _ptr_array(rcons), ys, xs, qa, lens)
     if rc < 0:
         raise HevceError(rc, "HEVCImageEncoderBatch")
+    if not copy_streams:
+        return [outs[i][: lens[i]] for i in range(n)], rcons
     return [outs[i][: lens[i]].tobytes() for i in range(n)], rcons
 
 
