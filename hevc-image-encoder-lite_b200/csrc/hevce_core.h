@@ -791,12 +791,12 @@ HEVCE_HD inline void scan_groups(const s16* lev, int s, unsigned& mlo, unsigned&
 }
 
 
-// trial lanes: thread -> candidate.  Modes 0..31 of a step share a warp, the 3 leftover modes are packed behind.
-HEVCE_HD inline int lane_to_cand(int nsteps, int t) {   // returns step*35+mode, or -1
-    if (t < nsteps * 32) return (t >> 5) * NMODE + (t & 31);
-    const int r = t - nsteps * 32;
-    if (r >= nsteps * 3) return -1;
-    return (r / 3) * NMODE + 32 + r % 3;
+// trial lanes: thread -> candidate.  The n lanes are spread evenly over the picture's four warps: the coders are
+// latency-bound and diverge, so fewer lanes per warp means less serialisation (and fewer warp-wide byte-release events).
+HEVCE_HD inline int lane_to_cand(int n, int t) {   // returns the candidate index < n, or -1
+    const int per = (n + 3) >> 2, w = t >> 5, l = t & 31;
+    const int c = w * per + l;
+    return (l < per && c < n) ? c : -1;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1258,10 +1258,11 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         if (S == 8) run_phase_c<4>(sc, g2, i0 + i1, q);
         PHASE_END_T(P_C);
         // ---- phase D (+ the trial coders that only need the levels of phase C)
-        constexpr int ND = S == 8 ? NT - NMODE : NT;   // 8x8 nodes: the last 35 threads code the NxN PU modes of this round
+        constexpr int ND = S == 8 ? NT / 2 : NT;   // 8x8 nodes: warps 2,3 code the 35 NxN PU modes of this round (18 + 17 lanes)
         if (S == 8) {
             PAR_FOR(t, NT) {
-                if (t >= ND) trial_lane<S>(sm, sc, 2 * NMODE + t - ND, depth, gtL + gtA, pmL, pmA);
+                const int l = t & 31, m = (t >> 5) == 2 ? l : 18 + l;
+                if (t >= ND && l < 18 && m < NMODE) trial_lane<S>(sm, sc, 2 * NMODE + m, depth, gtL + gtA, pmL, pmA);
             }
         }
         if (g0.n) run_phase_d<S>(sc, g0, 0, ND);
@@ -1290,7 +1291,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
 
     // ---- all 70 one-TU / four-TU trial coders; for 8x8 nodes a spare thread codes the NxN CU as a whole meanwhile
     PAR_FOR(t, NT) {
-        const int cand = lane_to_cand(2, t);
+        const int cand = lane_to_cand(2 * NMODE, t);
         if (cand >= 0) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);
         else if (S == 8 && t == NT - 1) {   // HEVCe.c:1531-1544
             Bac b = make_bac(sm.snap[depth]);
