@@ -791,12 +791,10 @@ HEVCE_HD inline void scan_groups(const s16* lev, int s, unsigned& mlo, unsigned&
 }
 
 
-// trial lanes: thread -> candidate.  The n lanes are spread evenly over the picture's four warps: the coders are
-// latency-bound and diverge, so fewer lanes per warp means less serialisation (and fewer warp-wide byte-release events).
+// trial lanes: thread -> candidate, packed into as few warps as possible.  (Spreading the 70 lanes evenly over the
+// four warps was measured 12 % slower: the trial phase is issue-bound, a warp instruction costs the same with 18 lanes.)
 HEVCE_HD inline int lane_to_cand(int n, int t) {   // returns the candidate index < n, or -1
-    const int per = (n + 3) >> 2, w = t >> 5, l = t & 31;
-    const int c = w * per + l;
-    return (l < per && c < n) ? c : -1;
+    return t < n ? t : -1;
 }
 
 // ------------------------------------------------------------------------------------------------------------
