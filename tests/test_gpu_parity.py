@@ -172,3 +172,29 @@ def test_raised_limit_extension(H):
     n = lib.HEVCImageEncoder(buf.ctypes.data_as(u8p), strip.ctypes.data_as(u8p), rc.ctypes.data_as(u8p), ctypes.byref(ys), ctypes.byref(xs), 2)
     assert (ys.value, xs.value) == (64, 8256) == r.shape
     assert s == buf[:n].tobytes() and np.array_equal(r, rc)
+
+
+def test_wide_and_tall_pictures(H):
+    """Long CTU rows / columns (map line buffer, above-right availability at the right edge, ragged last CTU)."""
+    wide = WL.config4_image(0)[:70, :2150]
+    tall = np.ascontiguousarray(WL.config4_image(1)[:2100, :50])
+    streams, rcons = H.HEVCImageEncoderBatch([wide, tall], [3, 1])
+    lib = checker()
+    for im, q, s, r in zip((wide, tall), (3, 1), streams, rcons):
+        ws, wr = R.encode_with(lib, im, q)
+        assert s == ws and np.array_equal(r, wr), im.shape
+
+
+@pytest.mark.slow
+def test_config4_one_4k_picture(H):
+    """BASELINE.json configs[3]: one synthetic 3840x2160 picture (padded to 3840x2176, 8,160 CTUs) at qpd6=4 against the
+    live CPU checker (~5 CPU-minutes; opt-in with HEVCE_SLOW=1).  Large single pictures are latency-bound by design."""
+    import time
+    img = WL.config4_image(0)
+    t0 = time.time()
+    s, r = H.HEVCImageEncoder(img, 4)
+    t1 = time.time()
+    ws, wr = R.encode_with(checker(), img, 4)
+    t2 = time.time()
+    print(f"config4: GPU {t1 - t0:.1f} s, CPU checker {t2 - t1:.1f} s, {len(s)} bytes")
+    assert r.shape == (2176, 3840) and s == ws and np.array_equal(r, wr)
