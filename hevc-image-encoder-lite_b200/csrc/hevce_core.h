@@ -429,6 +429,8 @@ struct Shared {
     u8 kind[16];                        // per 8x8 unit: 0 one TU, 1 four TUs, 2 NxN
     Coder live, snap[3], nxn_coder;
     s16* ctu_lev;                       // level store of the current CTU (Job::levs + ctu*1024)
+    Scratch sc;                         // this picture slot's global scratch (trial lanes may run on another picture's threads)
+    int q;                              // qpd6
     int cand_sse[NCAND], cand_bits[NCAND];
     unsigned cgnz[NCAND][4];            // non-zero-group bitmaps: one-TU: [0],[1] = low/high word; else [tu]
     int rate6[6];                       // RDOQ: weighted rate of levels 0..5
@@ -450,13 +452,16 @@ HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CO
 extern __shared__ __align__(16) unsigned char hevce_smem[];
 __device__ __forceinline__ Shared& my_sm() { return reinterpret_cast<Shared*>(hevce_smem)[threadIdx.x / NT]; }
 __device__ __forceinline__ Tables& my_tb() { return *reinterpret_cast<Tables*>(hevce_smem + GANG * sizeof(Shared)); }
+__device__ __forceinline__ Shared& gang_sm(int p) { return reinterpret_cast<Shared*>(hevce_smem)[p]; }
 #elif defined(__CUDACC__)
 inline Shared& my_sm() { return *static_cast<Shared*>(nullptr); }   // host pass of nvcc: declared, never executed
+inline Shared& gang_sm(int) { return *static_cast<Shared*>(nullptr); }
 inline Tables& my_tb() { return *static_cast<Tables*>(nullptr); }
 #else
 extern Shared* g_sim_sm;                                             // CTA simulator (tests/sim)
 extern Tables* g_sim_tb;
 inline Shared& my_sm() { return *g_sim_sm; }
+inline Shared& gang_sm(int) { return *g_sim_sm; }
 inline Tables& my_tb() { return *g_sim_tb; }
 #endif
 static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail too small");
@@ -470,6 +475,11 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 #define PAR_FOR(item, n) for (int item = HEVCE_TID; item < (n); item += NT)
 #define PAR_FOR_OFF(item, n, off) for (int item = (HEVCE_TID + NT - ((off) & (NT - 1))) & (NT - 1); item < (n); item += NT)
 #define PAR_FOR_SUB(item, n, nthr) for (int item = HEVCE_TID < (nthr) ? HEVCE_TID : (n); item < (n); item += (nthr))   // first nthr threads only
+// Trial-coder lanes are packed across the pictures of the gang (full warps): lane L of the CTA, or lane u of the
+// "upper half" threads (threads 64..127 of every picture) while the lower halves run phase-D items.
+#define GANG_RT GANG
+#define GANG_FOR(L, n) for (int L = (int)threadIdx.x; L < (n); L += NT * GANG)
+#define GANG_FOR_UPPER(u, n) for (int u = HEVCE_TID >= NT / 2 ? (int)(threadIdx.x / NT) * (NT / 2) + HEVCE_TID - NT / 2 : (n); u < (n); u += GANG * NT / 2)
 #define PHASE_END() __syncthreads()
 #if defined(HEVCE_PROFILE)   // per-phase latency histogram (development builds only)
 extern __device__ unsigned long long g_phase_cycles[16];
@@ -494,6 +504,9 @@ inline int sim_item(int i, int n) {
 #define PAR_FOR(item, n) for (int item##_i = 0, item = 0; item##_i < (n) && ((item = sim_item(item##_i, (n))), true); item##_i++)
 #define PAR_FOR_OFF(item, n, off) PAR_FOR(item, n)
 #define PAR_FOR_SUB(item, n, nthr) PAR_FOR(item, n)
+#define GANG_RT 1
+#define GANG_FOR(L, n) PAR_FOR(L, n)
+#define GANG_FOR_UPPER(u, n) PAR_FOR(u, n)
 #define PHASE_END() ((void)0)
 #define PHASE_END_T(tag) ((void)0)
 #define HEVCE_ATOMIC_OR(p, v) (*(p) |= (v))
@@ -713,11 +726,11 @@ inline CommitShared& my_csm() { return *g_sim_csm; }
 #endif
 struct MainEnv {
     HEVCE_HD static const Tables& tables() { return my_tb(); }
-    HEVCE_HD static u8* base() { return (u8*)&my_sm(); }
+    HEVCE_HD static u8* base(int p) { return (u8*)&gang_sm(p); }   // p: picture of the gang the lane works for
 };
 struct CommitEnv {
     HEVCE_HD static const Tables& tables() { return my_csm().tb; }
-    HEVCE_HD static u8* base() { return (u8*)&my_csm(); }
+    HEVCE_HD static u8* base(int) { return (u8*)&my_csm(); }
 };
 
 // One coding unit (HEVCe.c:1272-1340, 943-947).
@@ -732,9 +745,9 @@ struct CuDesc {
 };
 
 template <class BAC, class ENV>
-HEVCE_HD HEVCE_NOINLINE void code_cu(BAC& bio, int cx_off, int cx_s4, const CuDesc& d) {
+HEVCE_HD HEVCE_NOINLINE void code_cu(BAC& bio, int pic, int cx_off, int cx_s4, const CuDesc& d) {
     const Tables& tbl = ENV::tables();
-    const Cx cx = {ENV::base() + cx_off, cx_s4};
+    const Cx cx = {ENV::base(pic) + cx_off, cx_s4};
     BAC b = bio;   // coder state in registers for the whole CU
     const int s = d.s, kind = d.kind;
     if (kind != 3) {
@@ -1151,7 +1164,11 @@ HEVCE_HD inline int sm_off(const Shared& sm, const void* p) { return (int)((cons
 // One trial-coder lane: candidates 0..69 code the whole CU from the node snapshot (HEVCe.c:1434-1438, 1470-1474);
 // candidates 70..104 are NxN PU modes: residual alone from a fresh coder and fresh contexts (HEVCe.c:1505-1519).
 template <int S>
-HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int cand, int depth, int split_ctx, int pmL, int pmA) {
+HEVCE_HD inline void trial_lane(Shared& sm, int pic, int cand, int depth, int y0, int x0) {
+    const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
+    const int split_ctx = (S > sm.msz[my * 9 + mx - 1]) + (S > sm.msz[(my - 1) * 9 + mx]);
+    const int pmL = sm.mpm[my * 9 + mx - 1], pmA = sm.mpm[(my - 1) * 9 + mx];
+    const Scratch& sc = sm.sc;
     constexpr int H = S / 2;
     const bool pu = cand >= 2 * NMODE;
     const int slot = pu ? cand - 2 * NMODE : cand;   // context-set lane
@@ -1181,9 +1198,30 @@ HEVCE_HD inline void trial_lane(Shared& sm, const Scratch& sc, int cand, int dep
     } else {
         d.lev[0] = lev; d.mlo[0] = sm.cgnz[cand][0]; d.mhi = pu ? 0u : sm.cgnz[cand][1];
     }
-    code_cu<Bac, MainEnv>(b, sm_off(sm, sm.lane_ctx + slot), 4 * NLANE, d);
+    code_cu<Bac, MainEnv>(b, pic, sm_off(sm, sm.lane_ctx + slot), 4 * NLANE, d);
     sm.cand_bits[cand] = coder_len(b.c) - base_len;
     if (!pu) cand_coder(sm)[cand] = b.c;
+}
+
+// The NxN CU as a whole, trial-coded from the node snapshot (HEVCe.c:1531-1544)
+HEVCE_HD inline void nxn_trial(Shared& sm, int pic, int depth, int y0, int x0) {
+    const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
+    const int pmL = sm.mpm[my * 9 + mx - 1], pmA = sm.mpm[(my - 1) * 9 + mx];
+    Bac b = make_bac(sm.snap[depth]);
+    for (int i = 0; i < CTXW; i++) ((u32*)sm.nxn_ctx)[i] = ((const u32*)sm.snap_ctx[depth])[i];
+    CuDesc d;
+    d.s = 8; d.kind = 2; d.split_ctx = (8 > sm.msz[my * 9 + mx - 1]) + (8 > sm.msz[(my - 1) * 9 + mx]); d.mhi = 0;
+    for (int k = 0; k < 4; k++) { d.pm[k] = sm.nxn_pm[k]; d.lev[k] = sm.nxn_lev[k]; d.mlo[k] = sm.nxn_nz[k]; }
+    d.pl[0] = pmL;     d.pa[0] = pmA;
+    d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
+    d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
+    d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
+    code_cu<Bac, MainEnv>(b, pic, sm_off(sm, sm.nxn_ctx), 4, d);
+    int sse = 0;
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) { const int dd = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += dd * dd; }
+    sm.nxn_cost = rd_cost(rd_consts(sm.q), sse, coder_len(b.c) - coder_len(sm.snap[depth]));
+    sm.nxn_coder = b.c;
 }
 
 // Evaluate the non-split candidates of one CU node and adopt the winner (HEVCe.c:1420-1559).
@@ -1256,11 +1294,11 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         if (S == 8) run_phase_c<4>(sc, g2, i0 + i1, q);
         PHASE_END_T(P_C);
         // ---- phase D (+ the trial coders that only need the levels of phase C)
-        constexpr int ND = S == 8 ? NT / 2 : NT;   // 8x8 nodes: warps 2,3 code the 35 NxN PU modes of this round (18 + 17 lanes)
-        if (S == 8) {
-            PAR_FOR(t, NT) {
-                const int l = t & 31, m = (t >> 5) == 2 ? l : 18 + l;
-                if (t >= ND && l < 18 && m < NMODE) trial_lane<S>(sm, sc, 2 * NMODE + m, depth, gtL + gtA, pmL, pmA);
+        constexpr int ND = S == 8 ? NT / 2 : NT;   // 8x8 nodes: the upper half of every picture's threads hosts NxN PU coders
+        if (S == 8) {   // NxN PU coders of this round, all pictures of the gang, packed into full warps
+            GANG_FOR_UPPER(u, GANG_RT * NMODE) {
+                const int pic = u / NMODE, m = u - pic * NMODE;
+                trial_lane<S>(gang_sm(pic), pic, 2 * NMODE + m, depth, y0, x0);
             }
         }
         if (g0.n) run_phase_d<S>(sc, g0, 0, ND);
@@ -1287,26 +1325,15 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         }
     }
 
-    // ---- all 70 one-TU / four-TU trial coders; for 8x8 nodes a spare thread codes the NxN CU as a whole meanwhile
-    PAR_FOR(t, NT) {
-        const int cand = lane_to_cand(2 * NMODE, t);
-        if (cand >= 0) trial_lane<S>(sm, sc, cand, depth, gtL + gtA, pmL, pmA);
-        else if (S == 8 && t == NT - 1) {   // HEVCe.c:1531-1544
-            Bac b = make_bac(sm.snap[depth]);
-            for (int i = 0; i < CTXW; i++) ((u32*)sm.nxn_ctx)[i] = ((const u32*)sm.snap_ctx[depth])[i];
-            CuDesc d;
-            d.s = S; d.kind = 2; d.split_ctx = gtL + gtA; d.mhi = 0;
-            for (int k = 0; k < 4; k++) { d.pm[k] = sm.nxn_pm[k]; d.lev[k] = sm.nxn_lev[k]; d.mlo[k] = sm.nxn_nz[k]; }
-            d.pl[0] = pmL;     d.pa[0] = pmA;
-            d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
-            d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
-            d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
-            code_cu<Bac, MainEnv>(b, sm_off(sm, sm.nxn_ctx), 4, d);
-            int sse = 0;
-            for (int y = 0; y < 8; y++)
-                for (int x = 0; x < 8; x++) { const int dd = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += dd * dd; }
-            sm.nxn_cost = rd_cost(rk, sse, coder_len(b.c) - coder_len(sm.snap[depth]));
-            sm.nxn_coder = b.c;
+    // ---- all one-TU / four-TU trial coders of the gang (70 per picture), packed step-major into full warps; for 8x8
+    // nodes one more lane per picture codes the NxN CU as a whole
+    {
+        constexpr int NC = GANG_RT * NMODE;
+        GANG_FOR(L, 2 * NC + (S == 8 ? GANG_RT : 0)) {
+            if (L < 2 * NC) {
+                const int step = L >= NC, r = L - step * NC, pic = r / NMODE, m = r - pic * NMODE;
+                trial_lane<S>(gang_sm(pic), pic, step * NMODE + m, depth, y0, x0);
+            } else nxn_trial(gang_sm(L - 2 * NC), L - 2 * NC, depth, y0, x0);
         }
     }
     PHASE_END_T(P_TRIAL);
@@ -1404,7 +1431,7 @@ HEVCE_HD inline void commit_cu(BacCommit& b, int cx_off, int cx_s4, const CtuRec
     if (d.kind == 0) { d.lev[0] = lev; scan_groups(lev, s, d.mlo[0], d.mhi); }
     else
         for (int k = 0; k < 4; k++) { unsigned hi; d.lev[k] = lev + k * h * h; scan_groups(d.lev[k], h, d.mlo[k], hi); }
-    code_cu<BacCommit, CommitEnv>(b, cx_off, cx_s4, d);
+    code_cu<BacCommit, CommitEnv>(b, 0, cx_off, cx_s4, d);
 }
 
 HEVCE_HD inline void commit_ctu(const Job& job, int ctu, int lane) {
@@ -1502,6 +1529,8 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
     PAR_FOR(one, 1) {
         coder_reset(sm.live);
         sm.error = 0;
+        sm.sc = sc;
+        sm.q = q;
         sm.stream_pos = write_header(job.out, q, H, W);
     }
     PHASE_END_T(P_MISC);
