@@ -843,45 +843,63 @@ template <int T> struct Dim {
 
 // phase 0: reference samples (HEVCe.c:196-257) into the unified border array b[0..4T]: b[2T] = corner,
 // b[2T-1-i] = left[i], b[2T+1+i] = top[i]; the [1 2 1] filter is then uniform over the array.
+// One work item = one border index j for ALL candidates of the group: where sample j comes from (window, the
+// candidate's own sub-TU edges, or the constant 128) does not depend on the candidate, so it is resolved once and the
+// candidate loop is a uniform fetch / filter / store.
+struct BSrc { int kind, off; };   // kind 0: constant 128, 1: window byte offset, 2: offset inside the candidate's edge block
+
 template <int T>
-HEVCE_HD inline void border_item(Shared& sm, const Grp& g, int item) {
-    constexpr int NB = 4 * T + 1, BS = Dim<T>::BS;
-    const int which = item / NB, j = item - which * NB;   // private: candidate index; shared: 0 unfiltered / 1 filtered
-    const int cand = g.priv ? which : 0;
-    auto nb = [&](int y, int x) -> int {
+HEVCE_HD inline void border_column(Shared& sm, const Grp& g, int j) {
+    constexpr int BS = Dim<T>::BS;
+    const Avail& a = g.av;
+    auto pos = [&](int y, int x) -> BSrc {
         const int yy = g.ty + y, xx = g.tx + x;
-        if (g.priv) {   // inside the CU only the sub-TU edges can be asked for: row H-1 (bottom of TU 0/1) or column H-1 (right of TU 0/2)
+        if (g.priv) {   // inside the CU only the sub-TU edges can be asked for: row T-1 (bottom of TU 0/1) or column T-1 (right of TU 0/2)
             const int cy = yy - g.cuy, cx = xx - g.cux;
             if (cy >= 0 && cx >= 0 && cy < g.cus && cx < g.cus) {
-                const u8* e = sm.pool + g.rec + cand * (4 * T);
-                if (cy == T - 1) return e[(cx >= T ? T : 0) + (cx & (T - 1))];
-                return e[2 * T + (cy >= T ? T : 0) + (cy & (T - 1))];
+                if (cy == T - 1) return BSrc{2, (cx >= T ? T : 0) + (cx & (T - 1))};
+                return BSrc{2, 2 * T + (cy >= T ? T : 0) + (cy & (T - 1))};
             }
         }
-        return HEVCE_WIN(sm, yy, xx);
+        return BSrc{1, (1 + yy) * WP + 1 + xx};
     };
-    const Avail& a = g.av;
-    auto cor = [&]() -> int {   // HEVCe.c:212-219; only evaluated for the corner itself or as a substitute
-        if (a.L && a.A) return nb(-1, -1);
-        if (a.L) return nb(0, -1);
-        if (a.A) return nb(-1, 0);
-        return 128;
+    auto corner = [&]() -> BSrc {   // HEVCe.c:212-219
+        if (a.L && a.A) return pos(-1, -1);
+        if (a.L) return pos(0, -1);
+        if (a.A) return pos(-1, 0);
+        return BSrc{0, 0};
     };
-    auto u = [&](int jj) -> int {
-        if (jj == 2 * T) return cor();
+    auto resolve = [&](int jj) -> BSrc {   // HEVCe.c:221-243
+        if (jj == 2 * T) return corner();
         if (jj < 2 * T) {
             const int i = 2 * T - 1 - jj;
-            if (i < T ? a.L : a.LB) return nb(i, -1);
-            return a.L ? nb(T - 1, -1) : cor();
+            if (i < T ? a.L : a.LB) return pos(i, -1);
+            return a.L ? pos(T - 1, -1) : corner();
         }
         const int i = jj - 2 * T - 1;
-        if (i < T ? a.A : a.AR) return nb(-1, i);
-        return a.A ? nb(-1, T - 1) : cor();
+        if (i < T ? a.A : a.AR) return pos(-1, i);
+        return a.A ? pos(-1, T - 1) : corner();
     };
-    int v = u(j);
-    const bool filt = g.priv ? use_filtered(T, g.mode0 + cand) != 0 : which == 1;
-    if (T > 4 && filt && j > 0 && j < 4 * T) v = (2 + 2 * v + u(j - 1) + u(j + 1)) >> 2;
-    sm.pool[g.bord + which * BS + 1 + j] = (u8)v;
+    const bool inner = T > 4 && j > 0 && j < 4 * T;   // the two ends stay unfiltered (HEVCe.c:255-256); 4x4 is never filtered
+    const BSrc s0 = resolve(j);
+    BSrc sa = s0, sb = s0;
+    if (inner) { sa = resolve(j - 1); sb = resolve(j + 1); }
+    const u8* win = sm.win;
+    if (!g.priv) {
+        auto fetch = [&](const BSrc& q) -> int { return q.kind == 1 ? win[q.off] : 128; };
+        const int v = fetch(s0);
+        sm.pool[g.bord + 1 + j] = (u8)v;
+        if (T > 4) sm.pool[g.bord + BS + 1 + j] = (u8)(inner ? (2 + 2 * v + fetch(sa) + fetch(sb)) >> 2 : v);
+    } else {
+        const u8* edges = sm.pool + g.rec;
+        auto fetch = [&](const BSrc& q, int c) -> int { return q.kind == 1 ? win[q.off] : q.kind == 2 ? edges[c * (4 * T) + q.off] : 128; };
+        u8* dst = sm.pool + g.bord + 1 + j;
+        for (int c = 0; c < g.n; c++) {
+            int v = fetch(s0, c);
+            if (inner && use_filtered(T, g.mode0 + c)) v = (2 + 2 * v + fetch(sa, c) + fetch(sb, c)) >> 2;
+            dst[c * BS] = (u8)v;
+        }
+    }
 }
 
 // phase A: prediction of column x (HEVCe.c:262-381), residual, forward column transform (HEVCe.c:514)
@@ -1089,8 +1107,7 @@ HEVCE_HD HEVCE_NOINLINE void run_borders(const Grp& gref, int off) {
     Shared& sm = my_sm();
     const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
     if (g.n == 0) return;
-    const int n = (g.priv ? g.n : (T > 4 ? 2 : 1)) * (4 * T + 1);
-    PAR_FOR_OFF(item, n, off) border_item<T>(sm, g, item);
+    PAR_FOR_OFF(j, 4 * T + 1, off) border_column<T>(sm, g, j);
 }
 template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_phase_a(const Grp& gref, int off) {
@@ -1275,8 +1292,8 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         const int i0 = g0.n * S, i1 = g1.n * H;
         // ---- phase 0: reference samples
         run_borders<S>(g0, 0);
-        run_borders<H>(g1, 2 * (4 * S + 1));
-        if (S == 8) run_borders<4>(g2, 2 * (4 * S + 1) + g1.n * (4 * H + 1));
+        run_borders<H>(g1, 4 * S + 1);
+        if (S == 8) run_borders<4>(g2, 4 * S + 1 + 4 * H + 1);
         PHASE_END_T(P_BORDER);
         // ---- phase A
         if (g0.n) run_phase_a<S>(g0, 0);
