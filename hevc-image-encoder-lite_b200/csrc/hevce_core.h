@@ -902,61 +902,13 @@ HEVCE_HD inline void border_column(Shared& sm, const Grp& g, int j) {
     }
 }
 
-// prediction of column x of a TxT block into registers (HEVCe.c:262-381).  B[k]: k > 0 top[k-1], k < 0 left[-k-1], 0 corner
-template <int T>
-HEVCE_HD inline void predict_column(const u8* B, int m, int x, int (&v)[T]) {
-    constexpr int LG = Dim<T>::LG, UNR = Dim<T>::UNR;
-    const bool edge = T <= 16;
-    if (m == 0) {
-        const int tr = B[T + 1], bl = B[-T - 1], tx = B[1 + x];
-#pragma unroll
-        for (int y = 0; y < T; y++) v[y] = ((T - 1 - x) * B[-1 - y] + (x + 1) * tr + (T - 1 - y) * tx + (y + 1) * bl + T) >> (LG + 1);
-    } else if (m == 1) {
-        int dc = T;
-#pragma unroll UNR
-        for (int i = 0; i < T; i++) dc += B[-1 - i] + B[1 + i];
-        dc >>= LG + 1;
-#pragma unroll
-        for (int y = 0; y < T; y++) v[y] = (edge && x == 0 && y > 0) ? (2 + 3 * dc + B[-1 - y]) >> 2 : dc;
-        if (edge) v[0] = x == 0 ? (2 + 2 * dc + B[-1] + B[1]) >> 2 : (2 + 3 * dc + B[1 + x]) >> 2;
-    } else if (m == 10) {
-#pragma unroll
-        for (int y = 0; y < T; y++) v[y] = B[-1 - y];
-        if (edge) v[0] = iclip(((B[1 + x] - B[0]) >> 1) + B[-1], 0, 255);
-    } else if (m == 26) {
-        const int t = B[1 + x];
-#pragma unroll
-        for (int y = 0; y < T; y++) v[y] = (edge && x == 0) ? iclip(((B[-1 - y] - B[0]) >> 1) + t, 0, 255) : t;
-    } else {
-        const int ang = intra_angle(m), aa = iabs(ang), inv = (8192 + aa / 2) / aa;   // HEVCe.c:283
-        if (m < 18) {   // horizontal family: main arm = left, projected side = top
-            const int off = ang * (x + 1), oi = off >> 5, of = off & 31;
-            auto R = [&](int k) -> int { return k >= 0 ? B[-k] : B[(128 - inv * k) >> 8]; };
-            int prev = R(oi + 1);
-#pragma unroll
-            for (int y = 0; y < T; y++) {
-                const int nxt = R(oi + y + 2);
-                v[y] = ((32 - of) * prev + of * nxt + 16) >> 5;
-                prev = nxt;
-            }
-        } else {        // vertical family: main arm = top, projected side = left
-            auto R = [&](int k) -> int { return k >= 0 ? B[k] : B[-((128 - inv * k) >> 8)]; };
-#pragma unroll
-            for (int y = 0; y < T; y++) {
-                const int off = ang * (y + 1), oi = off >> 5, of = off & 31, k = oi + x + 1;
-                v[y] = ((32 - of) * R(k) + of * R(k + 1) + 16) >> 5;
-            }
-        }
-    }
-}
-
-// phase A: prediction of column x, residual, forward column transform (HEVCe.c:514)
+// phase A: prediction of column x (HEVCe.c:262-381), residual, forward column transform (HEVCe.c:514)
 template <int T>
 HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
-    constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, BS = Dim<T>::BS;
+    constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, BS = Dim<T>::BS, UNR = Dim<T>::UNR;
     const int c = item >> LG, x = item & (T - 1), m = g.mode0 + c;
     const int bsel = g.priv ? c : (T > 4 && use_filtered(T, m));
-    const u8* B = sm.pool + g.bord + bsel * BS + 1 + 2 * T;
+    const u8* B = sm.pool + g.bord + bsel * BS + 1 + 2 * T;   // B[k]: k > 0 top[k-1], k < 0 left[-k-1], 0 corner
     const u8* org = sm.orig + g.ty * CTU + g.tx + x;
     u8* pp = sm.pool + g.pred + c * (T * T) + x;
     if (x == 0) {   // per-candidate accumulators of this TU
@@ -964,134 +916,56 @@ HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
         if (g.one_tu) { sm.cgnz[ci][0] = 0; sm.cgnz[ci][1] = 0; sm.cand_sse[ci] = 0; }
         else { sm.cgnz[ci][g.tu] = 0; if (g.tu == 0 || !g.priv) sm.cand_sse[ci] = 0; }
     }
-    int v[T], o[T];
-    predict_column<T>(B, m, x, v);
-#pragma unroll
-    for (int y = 0; y < T; y++) {
-        pp[y * T] = (u8)v[y];
-        v[y] = (int)org[y * CTU] - v[y];
+    const bool edge = T <= 16;
+    if (m == 0) {
+        const int tr = B[T + 1], bl = B[-T - 1], tx = B[1 + x];
+#pragma unroll UNR
+        for (int y = 0; y < T; y++) pp[y * T] = (u8)(((T - 1 - x) * B[-1 - y] + (x + 1) * tr + (T - 1 - y) * tx + (y + 1) * bl + T) >> (LG + 1));
+    } else if (m == 1) {
+        int dc = T;
+#pragma unroll UNR
+        for (int i = 0; i < T; i++) dc += B[-1 - i] + B[1 + i];
+        dc >>= LG + 1;
+#pragma unroll UNR
+        for (int y = 0; y < T; y++) pp[y * T] = (u8)((edge && x == 0 && y > 0) ? (2 + 3 * dc + B[-1 - y]) >> 2 : dc);
+        if (edge) pp[0] = (u8)(x == 0 ? (2 + 2 * dc + B[-1] + B[1]) >> 2 : (2 + 3 * dc + B[1 + x]) >> 2);
+    } else if (m == 10) {
+#pragma unroll UNR
+        for (int y = 0; y < T; y++) pp[y * T] = B[-1 - y];
+        if (edge) pp[0] = (u8)iclip(((B[1 + x] - B[0]) >> 1) + B[-1], 0, 255);
+    } else if (m == 26) {
+        const int t = B[1 + x];
+#pragma unroll UNR
+        for (int y = 0; y < T; y++) pp[y * T] = (u8)((edge && x == 0) ? iclip(((B[-1 - y] - B[0]) >> 1) + t, 0, 255) : t);
+    } else {
+        const int ang = intra_angle(m), aa = iabs(ang), inv = (8192 + aa / 2) / aa;   // HEVCe.c:283
+        if (m < 18) {   // horizontal family: main arm = left, projected side = top
+            const int off = ang * (x + 1), oi = off >> 5, of = off & 31;
+            auto R = [&](int k) -> int { return k >= 0 ? B[-k] : B[(128 - inv * k) >> 8]; };
+            int prev = R(oi + 1);
+#pragma unroll UNR
+            for (int y = 0; y < T; y++) {
+                const int nxt = R(oi + y + 2);
+                pp[y * T] = (u8)(((32 - of) * prev + of * nxt + 16) >> 5);
+                prev = nxt;
+            }
+        } else {        // vertical family: main arm = top, projected side = left
+            auto R = [&](int k) -> int { return k >= 0 ? B[k] : B[-((128 - inv * k) >> 8)]; };
+#pragma unroll UNR
+            for (int y = 0; y < T; y++) {
+                const int off = ang * (y + 1), oi = off >> 5, of = off & 31, k = oi + x + 1;
+                pp[y * T] = (u8)(((32 - of) * R(k) + of * R(k + 1) + 16) >> 5);
+            }
+        }
     }
+    int v[T], o[T];
+#pragma unroll
+    for (int y = 0; y < T; y++) v[y] = (int)org[y * CTU] - (int)pp[y * T];
     Xf<T>::f(v, o);
     s16* bp = (s16*)(sm.pool + g.blk) + c * BLK + x;
     constexpr int A1 = LG - 1;
 #pragma unroll
     for (int k = 0; k < T; k++) bp[k * T] = (s16)((o[k] + (1 << A1 >> 1)) >> A1);
-}
-
-// A whole 4x4 TU by one thread, everything in registers: phases A-D fused (the four-TU candidates of 8x8 nodes and the
-// NxN PU candidates).  Same arithmetic as the phase items; 16 independent pixels per thread give the instruction-level
-// parallelism the line items lack, and three barriers per round disappear.
-HEVCE_HD inline void tu4_item(Shared& sm, const Scratch& sc, const Grp& g, int c, int q, const RdK& rk) {
-    constexpr int BS = Dim<4>::BS;
-    const int m = g.mode0 + c, ci = g.cand0 + c;
-    const u8* B = sm.pool + g.bord + (g.priv ? c : 0) * BS + 1 + 8;
-    const u8* org = sm.orig + g.ty * CTU + g.tx;
-    int pr[4][4], t1[4][4], lv[16];   // pr[x][y]
-    int v[4], o[4];
-#pragma unroll
-    for (int x = 0; x < 4; x++) {
-        predict_column<4>(B, m, x, pr[x]);
-#pragma unroll
-        for (int y = 0; y < 4; y++) v[y] = (int)org[y * CTU + x] - pr[x][y];
-        fdst4(v, o);
-#pragma unroll
-        for (int k = 0; k < 4; k++) t1[k][x] = (o[k] + 1) >> 1;
-    }
-    // forward rows + RDOQ (HEVCe.c:563-586), group zero-out (HEVCe.c:589-592)
-    const int sh = 19 + q, add = 1 << sh >> 1, thr = 9 << sh >> 2, wd = rk.wd, wb = rk.wb;
-    int sum = 0, nz = 0;
-#pragma unroll
-    for (int y = 0; y < 4; y++) {
-#pragma unroll
-        for (int x = 0; x < 4; x++) v[x] = t1[y][x];
-        fdst4(v, o);
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            const int cf = (o[x] + 128) >> 8;
-            const int dl = iabs(cf) << 14;
-            const int lvl = (dl + add) >> sh;
-            int pick = 0;
-            if (lvl > 0) {
-                int best = IMAX;
-                pick = lvl;
-#pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    const int l = lvl - t;
-                    const int d1 = iabs(dl - (l << sh)) >> 8;
-                    const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
-                    const int wr = l < 6 ? sm.rate6[imax(l, 0)] : wb * (92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15));
-                    const int cost = wd * d + wr;
-                    if (l >= 0 && cost < best) { best = cost; pick = l; }
-                }
-            }
-            lv[y * 4 + x] = cf < 0 ? -pick : pick;
-            nz |= pick;
-            sum += imin(dl, thr);
-        }
-    }
-    if (sum < thr) nz = 0;
-    // final levels -> store (scan order of the mode), bitmap
-    {
-        const u8* inv = my_tb().inv4[scan_type(4, m)];
-        s16* lp = sc.glev + (size_t)ci * LEV_STRIDE + g.tu * 16;
-#pragma unroll
-        for (int p = 0; p < 16; p++) { if (!nz) lv[p] = 0; lp[inv[p]] = (s16)lv[p]; }
-        sm.cgnz[ci][g.tu] = nz ? 1u : 0u;
-    }
-    // dequantisation (HEVCe.c:600-615), inverse transform, reconstruction, SSE
-    const int qs = 5 + q;
-    int sse = 0;
-    int rec[4][4];   // rec[y][x]
-    if (nz) {
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-#pragma unroll
-            for (int y = 0; y < 4; y++) v[y] = iclip(lv[y * 4 + x] * (1 << qs), -32768, 32767);
-            idst4(v, o);
-#pragma unroll
-            for (int k = 0; k < 4; k++) t1[k][x] = iclip((o[k] + 64) >> 7, -32768, 32767);
-        }
-    }
-#pragma unroll
-    for (int y = 0; y < 4; y++) {
-        if (nz) {
-#pragma unroll
-            for (int x = 0; x < 4; x++) v[x] = t1[y][x];
-            idst4(v, o);
-        }
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            const int res = nz ? iclip((o[x] + 2048) >> 12, -32768, 32767) : 0;
-            const int r = iclip(res + pr[x][y], 0, 255);
-            const int d = (int)org[y * CTU + x] - r;
-            rec[y][x] = r;
-            sse += d * d;
-        }
-    }
-    if (g.priv) {   // four-TU candidate: edges for its later sub-TUs + the global reconstruction store
-        u8* e = sm.pool + g.rec + c * 16;
-        if (g.tu < 2) {
-#pragma unroll
-            for (int x = 0; x < 4; x++) e[g.tu * 4 + x] = (u8)rec[3][x];
-        }
-        if (!(g.tu & 1)) {
-#pragma unroll
-            for (int y = 0; y < 4; y++) e[8 + (g.tu >> 1) * 4 + y] = (u8)rec[y][3];
-        }
-        u8* rg = sc.grec + (size_t)ci * (CTU * CTU) + (g.ty - g.cuy) * g.cus + (g.tx - g.cux);
-#pragma unroll
-        for (int y = 0; y < 4; y++)
-#pragma unroll
-            for (int x = 0; x < 4; x++) rg[y * g.cus + x] = (u8)rec[y][x];
-        sm.cand_sse[ci] = g.tu == 0 ? sse : sm.cand_sse[ci] + sse;
-    } else {        // NxN PU candidate: the PU's reconstruction (the winner goes to the window)
-        u8* rs = sm.pool + g.rec + c * 16;
-#pragma unroll
-        for (int y = 0; y < 4; y++)
-#pragma unroll
-            for (int x = 0; x < 4; x++) rs[y * 4 + x] = (u8)rec[y][x];
-        sm.cand_sse[ci] = sse;
-    }
 }
 
 // phase B: forward row transform (HEVCe.c:515) + per-coefficient RDOQ (HEVCe.c:563-586); tentative levels replace
@@ -1264,15 +1138,6 @@ HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, 
     else { PAR_FOR_OFF(item, g.n * T, off) phase_d_item<T>(sm, sc, g, item); }
 }
 
-template <int T4>   // template only so that the host pass of nvcc does not emit it
-HEVCE_HD HEVCE_NOINLINE void run_tu4(const Scratch& scref, const Grp& gref, int off, int q) {
-    Shared& sm = my_sm();
-    const Grp g = gref;
-    const Scratch sc = scref;
-    const RdK rk = rd_consts(q);
-    PAR_FOR_OFF(c, g.n, off) tu4_item(sm, sc, g, c, q, rk);
-}
-
 // shared-memory carve-up of the pool for a node of size S: group 0 = one-TU candidates (T = S), group 1 = four-TU
 // candidates (T = S/2), group 2 (S = 8 only) = NxN PU candidates (T = 4)
 template <int S> struct Plan {
@@ -1430,33 +1295,21 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         run_borders<H>(g1, 4 * S + 1);
         if (S == 8) run_borders<4>(g2, 4 * S + 1 + 4 * H + 1);
         PHASE_END_T(P_BORDER);
-        if (S == 8) {
-            // 8x8 nodes: the 4x4 TUs (four-TU candidates, NxN PU candidates) are done whole by one thread each in the
-            // phase-A slot; only the 35 one-TU candidates of round 0 need the B/C phases
-            if (g0.n) run_phase_a<S>(g0, 0);
-            run_tu4<4>(sc, g1, i0, q);
-            run_tu4<4>(sc, g2, i0 + NMODE, q);
-            PHASE_END_T(P_A);
-            if (g0.n) {
-                run_phase_b<S>(g0, 0, q);
-                PHASE_END_T(P_B);
-                run_phase_c<S>(sc, g0, 0, q);
-                PHASE_END_T(P_C);
-            }
-        } else {
-            // ---- phase A
-            if (g0.n) run_phase_a<S>(g0, 0);
-            if (g1.n) run_phase_a<H>(g1, i0);
-            PHASE_END_T(P_A);
-            // ---- phase B
-            if (g0.n) run_phase_b<S>(g0, 0, q);
-            if (g1.n) run_phase_b<H>(g1, i0, q);
-            PHASE_END_T(P_B);
-            // ---- phase C
-            if (g0.n) run_phase_c<S>(sc, g0, 0, q);
-            if (g1.n) run_phase_c<H>(sc, g1, i0, q);
-            PHASE_END_T(P_C);
-        }
+        // ---- phase A
+        if (g0.n) run_phase_a<S>(g0, 0);
+        if (g1.n) run_phase_a<H>(g1, i0);
+        if (S == 8) run_phase_a<4>(g2, i0 + i1);
+        PHASE_END_T(P_A);
+        // ---- phase B
+        if (g0.n) run_phase_b<S>(g0, 0, q);
+        if (g1.n) run_phase_b<H>(g1, i0, q);
+        if (S == 8) run_phase_b<4>(g2, i0 + i1, q);
+        PHASE_END_T(P_B);
+        // ---- phase C
+        if (g0.n) run_phase_c<S>(sc, g0, 0, q);
+        if (g1.n) run_phase_c<H>(sc, g1, i0, q);
+        if (S == 8) run_phase_c<4>(sc, g2, i0 + i1, q);
+        PHASE_END_T(P_C);
         // ---- phase D (+ the trial coders that only need the levels of phase C)
         constexpr int ND = S == 8 ? NT / 2 : NT;   // 8x8 nodes: the upper half of every picture's threads hosts NxN PU coders
         if (S == 8) {   // NxN PU coders of this round, all pictures of the gang, packed into full warps
@@ -1466,7 +1319,8 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             }
         }
         if (g0.n) run_phase_d<S>(sc, g0, 0, ND);
-        if (S != 8 && g1.n) run_phase_d<H>(sc, g1, i0, ND);
+        if (g1.n) run_phase_d<H>(sc, g1, i0, ND);
+        if (S == 8) run_phase_d<4>(sc, g2, i0 + i1, ND);
         PHASE_END_T(P_D_TRIAL);
         if (S == 8) {
             PAR_FOR(one, 1) {   // best PU mode, last minimum wins (HEVCe.c:1521)
