@@ -18,6 +18,7 @@
 #define API __attribute__((visibility("default")))
 #define MAX_DEV 64
 #define CHUNK_PIXELS (768LL * 1024 * 1024)   /* per-device sub-batch bound (padded pixels) so staging stays modest */
+#define CHUNK_PICTURES 32768                  /* ... and pictures (the commit kernel's grid.y is the picture index) */
 
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static int g_ndev = -1, g_devs[MAX_DEV];
@@ -101,7 +102,7 @@ static void *shard_main(void *arg) {
     while (done < sh->count && sh->status == 0) {
         int a = sh->first + done, m = 0, rc;
         long long px = 0;
-        while (done + m < sh->count && (m == 0 || px + padded_pixels(sh->ysz[a + m], sh->xsz[a + m]) <= CHUNK_PIXELS)) {
+        while (done + m < sh->count && m < CHUNK_PICTURES && (m == 0 || px + padded_pixels(sh->ysz[a + m], sh->xsz[a + m]) <= CHUNK_PIXELS)) {
             px += padded_pixels(sh->ysz[a + m], sh->xsz[a + m]);
             m++;
         }
