@@ -180,7 +180,7 @@ static int stage_reserve(hevce_session* s, size_t need) {
 }
 
 extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, const int* xsz, const int* qpd6) {
-    if (!s || n < 0 || (n > 0 && (!ysz || !xsz || !qpd6))) return HEVCE_ERR_ARG;
+    if (!s || n < 0 || n > 65535 || (n > 0 && (!ysz || !xsz || !qpd6))) return HEVCE_ERR_ARG;   // grid.y of the commit kernel = picture index
     int rc = device_prepare(s->device);
     if (rc) return rc;
     const int max_dim = hevce_internal_max_dim();

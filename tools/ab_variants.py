@@ -26,9 +26,14 @@ if sys.argv[1] == "build":
         print(spec, "ok" if p.returncode == 0 else "FAILED\n" + out[-2000:])
 else:
     args = sys.argv[2:] or ["888", "64", "64", "2"]
-    code = ("import sys,os; sys.path.insert(0,'hevc-image-encoder-lite_b200'); sys.path.insert(0,'tests'); import hevce_b200 as H, workloads as WL;"
-            "H.LIB_PATH=sys.argv[1]; n,h,w,q=map(int,sys.argv[2:6]); imgs=[WL.config3_image(i)[100:100+h,200:200+w].copy() for i in range(n)];"
-            "s=H.Session(0,[i.shape for i in imgs],q); s.upload(imgs); ms=[s.encode() for _ in range(4)]; print(os.path.basename(sys.argv[1]), ' '.join('%.2f'%m for m in ms))")
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import workloads as WL
+    n, h, w, q = map(int, args)
+    np.save("/tmp/ab_inputs.npy", np.stack([WL.config3_image(i)[100:100 + h, 200:200 + w] for i in range(n)]))   # generated once
+    code = ("import sys,os,numpy as np; sys.path.insert(0,'hevc-image-encoder-lite_b200'); import hevce_b200 as H;"
+            "H.LIB_PATH=sys.argv[1]; q=int(sys.argv[5]); a=np.load('/tmp/ab_inputs.npy'); imgs=[np.ascontiguousarray(x) for x in a];"
+            "s=H.Session(0,[i.shape for i in imgs],q); s.upload(imgs); ms=[s.encode() for _ in range(4)]; print(os.path.basename(sys.argv[1]), ' '.join('%.2f'%m for m in ms), flush=True)")
     for rep in range(2):
         for so in sorted(glob.glob(os.path.join(OUT, "*.so"))):
             subprocess.run([sys.executable, "-c", code, so] + args, cwd=ROOT)
