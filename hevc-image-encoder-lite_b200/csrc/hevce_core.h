@@ -477,7 +477,13 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 #define HEVCE_TID ((int)(threadIdx.x & (NT - 1)))
 #define PAR_FOR(item, n) for (int item = HEVCE_TID; item < (n); item += NT)
 #define PAR_FOR_OFF(item, n, off) for (int item = (HEVCE_TID + NT - ((off) & (NT - 1))) & (NT - 1); item < (n); item += NT)
-#define PAR_FOR_SUB(item, n, nthr) for (int item = HEVCE_TID < (nthr) ? HEVCE_TID : (n); item < (n); item += (nthr))   // first nthr threads only
+// threads [t0, t0 + nthr) of the picture only (nthr a power of two); item 0 starts at thread t0 + off
+#define PAR_FOR_TEAM(item, n, t0, nthr, off) for (int item = (unsigned)(HEVCE_TID - (t0)) < (unsigned)(nthr) ? ((HEVCE_TID - (t0) + (nthr) - ((off) & ((nthr) - 1))) & ((nthr) - 1)) : (n); item < (n); item += (nthr))
+// 8x8 nodes split every picture's threads into two teams of NT/2 that run independent phase chains; a team's barrier
+// spans the same team of all pictures of the gang (their trial lanes are packed across pictures)
+#define TEAM_A if (HEVCE_TID < NT / 2)
+#define TEAM_B else
+#define TEAM_SYNC(id) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(GANG * NT / 2) : "memory")
 // Trial-coder lanes are packed across the pictures of the gang (full warps): lane L of the CTA, or lane u of the
 // "upper half" threads (threads 64..127 of every picture) while the lower halves run phase-D items.
 #define GANG_RT GANG
@@ -506,7 +512,10 @@ inline int sim_item(int i, int n) {
 }
 #define PAR_FOR(item, n) for (int item##_i = 0, item = 0; item##_i < (n) && ((item = sim_item(item##_i, (n))), true); item##_i++)
 #define PAR_FOR_OFF(item, n, off) PAR_FOR(item, n)
-#define PAR_FOR_SUB(item, n, nthr) PAR_FOR(item, n)
+#define PAR_FOR_TEAM(item, n, t0, nthr, off) PAR_FOR(item, n)
+#define TEAM_A
+#define TEAM_B
+#define TEAM_SYNC(id) ((void)0)
 #define GANG_RT 1
 #define GANG_FOR(L, n) PAR_FOR(L, n)
 #define GANG_FOR_UPPER(u, n) PAR_FOR(u, n)
@@ -1116,40 +1125,40 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
 }
 
 // phase runners: one (non-inlined) copy per TU size, shared by all node sizes
+struct Team { int t0, nthr; };   // the threads of a picture that share a phase: [t0, t0 + nthr)
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_borders(const Grp& gref, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_borders(const Grp& gref, int off, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
     if (g.n == 0) return;
-    PAR_FOR_OFF(j, 4 * T + 1, off) border_column<T>(sm, g, j);
+    PAR_FOR_TEAM(j, 4 * T + 1, tm.t0, tm.nthr, off) border_column<T>(sm, g, j);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_a(const Grp& gref, int off) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_a(const Grp& gref, int off, Team tm) {
     Shared& sm = my_sm();
-    const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
-    PAR_FOR_OFF(item, g.n * T, off) phase_a_item<T>(sm, g, item);
+    const Grp g = gref;
+    PAR_FOR_TEAM(item, g.n * T, tm.t0, tm.nthr, off) phase_a_item<T>(sm, g, item);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_b(const Grp& gref, int off, int q) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_b(const Grp& gref, int off, int q, Team tm) {
     Shared& sm = my_sm();
-    const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
+    const Grp g = gref;
     const RdK rk = rd_consts(q);
-    PAR_FOR_OFF(item, g.n * T, off) phase_b_item<T>(sm, g, item, q, rk);
+    PAR_FOR_TEAM(item, g.n * T, tm.t0, tm.nthr, off) phase_b_item<T>(sm, g, item, q, rk);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_c(const Scratch& scref, const Grp& gref, int off, int q) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_c(const Scratch& scref, const Grp& gref, int off, int q, Team tm) {
     Shared& sm = my_sm();
-    const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
+    const Grp g = gref;
     const Scratch sc = scref;
-    PAR_FOR_OFF(item, g.n * T, off) phase_c_item<T>(sm, sc, g, item, q);
+    PAR_FOR_TEAM(item, g.n * T, tm.t0, tm.nthr, off) phase_c_item<T>(sm, sc, g, item, q);
 }
 template <int T>
-HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, int off, int nthr) {
+HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, int off, Team tm) {
     Shared& sm = my_sm();
-    const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
+    const Grp g = gref;
     const Scratch sc = scref;
-    if (nthr < NT) { PAR_FOR_SUB(item, g.n * T, nthr) phase_d_item<T>(sm, sc, g, item); }   // the other threads run trial coders meanwhile
-    else { PAR_FOR_OFF(item, g.n * T, off) phase_d_item<T>(sm, sc, g, item); }
+    PAR_FOR_TEAM(item, g.n * T, tm.t0, tm.nthr, off) phase_d_item<T>(sm, sc, g, item);
 }
 
 // shared-memory carve-up of the pool for a node of size S: group 0 = one-TU candidates (T = S), group 1 = four-TU
@@ -1275,85 +1284,127 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         }
     }
 
-    for (int r = 0; r < P::ROUNDS; r++) {
-        const int k = r & 3;              // sub-TU / PU index of this round
-        const int chunk = r >> 2;         // 32x32 nodes only: chunk of four-TU modes
-        // ---- group descriptors (uniform)
-        Grp g0, g1, g2;
-        {   // one-TU candidates: a slice of the 35 modes per round
-            int m0, n;
-            if (S == 8) { m0 = 0; n = r == 0 ? 35 : 0; }
-            else { m0 = r * P::N0; n = imax(0, imin(P::N0, NMODE - m0)); }
-            g0.n = n; g0.cand0 = m0; g0.mode0 = m0; g0.ty = y0; g0.tx = x0; g0.av = av; g0.priv = 0;
-            g0.cuy = y0; g0.cux = x0; g0.cus = S; g0.tu = 0; g0.one_tu = 1; g0.grec = 1;
-            g0.blk = P::BLK0; g0.pred = P::PRED0; g0.psum = P::PSUM0; g0.bord = P::BORD0;
-            g0.rec = -1; g0.rec_stride = 0; g0.rec_pitch = 0;
+    // ---- group descriptors (uniform over the threads of a picture)
+    auto group0 = [&](int r) -> Grp {   // one-TU candidates: a slice of the 35 modes per round
+        Grp g;
+        int m0, n;
+        if (S == 8) { m0 = 0; n = r == 0 ? 35 : 0; }
+        else { m0 = r * P::N0; n = imax(0, imin(P::N0, NMODE - m0)); }
+        g.n = n; g.cand0 = m0; g.mode0 = m0; g.ty = y0; g.tx = x0; g.av = av; g.priv = 0;
+        g.cuy = y0; g.cux = x0; g.cus = S; g.tu = 0; g.one_tu = 1; g.grec = 1;
+        g.blk = P::BLK0; g.pred = P::PRED0; g.psum = P::PSUM0; g.bord = P::BORD0;
+        g.rec = -1; g.rec_stride = 0; g.rec_pitch = 0;
+        return g;
+    };
+    auto group1 = [&](int r) -> Grp {   // four-TU candidates: sub-TU k of a chunk of modes, each with its own reconstruction as neighbour
+        Grp g;
+        const int k = r & 3, chunk = r >> 2;   // 32x32 nodes only: chunks of four-TU modes
+        const int m0 = chunk * P::N1, n = (S == 16 && r >= 4) ? 0 : imax(0, imin(P::N1, NMODE - m0));
+        g.n = n; g.cand0 = NMODE + m0; g.mode0 = m0; g.ty = y0 + (k >> 1) * H; g.tx = x0 + (k & 1) * H; g.av = sub_avail(av, k); g.priv = 1;
+        g.cuy = y0; g.cux = x0; g.cus = S; g.tu = k; g.one_tu = 0; g.grec = 1;
+        g.blk = P::BLK1; g.pred = P::PRED1; g.psum = P::PSUM1; g.bord = P::BORD1;
+        g.rec = P::REC1; g.rec_stride = 4 * H; g.rec_pitch = 0;
+        return g;
+    };
+    auto group2 = [&](int k) -> Grp {   // 8x8 nodes: NxN PU k, all 35 modes, neighbours from the window (earlier PUs' winners are already there)
+        Grp g;
+        g.n = 35; g.cand0 = 2 * NMODE; g.mode0 = 0; g.ty = y0 + (k >> 1) * 4; g.tx = x0 + (k & 1) * 4; g.av = sub_avail(av, k); g.priv = 0;
+        g.cuy = g.ty; g.cux = g.tx; g.cus = 4; g.tu = 0; g.one_tu = 0; g.grec = 0;
+        g.blk = P::BLK2; g.pred = P::PRED2; g.psum = P::PSUM2; g.bord = P::BORD2;
+        g.rec = P::REC2; g.rec_stride = 16; g.rec_pitch = 4;
+        return g;
+    };
+
+    if constexpr (S > 8) {
+        const Team all = {0, NT};
+        for (int r = 0; r < P::ROUNDS; r++) {
+            const Grp g0 = group0(r), g1 = group1(r);
+            const int i0 = g0.n * S;
+            // ---- phase 0: reference samples
+            run_borders<S>(g0, 0, all);
+            run_borders<H>(g1, 4 * S + 1, all);
+            PHASE_END_T(P_BORDER);
+            // ---- phase A
+            if (g0.n) run_phase_a<S>(g0, 0, all);
+            if (g1.n) run_phase_a<H>(g1, i0, all);
+            PHASE_END_T(P_A);
+            // ---- phase B
+            if (g0.n) run_phase_b<S>(g0, 0, q, all);
+            if (g1.n) run_phase_b<H>(g1, i0, q, all);
+            PHASE_END_T(P_B);
+            // ---- phase C
+            if (g0.n) run_phase_c<S>(sc, g0, 0, q, all);
+            if (g1.n) run_phase_c<H>(sc, g1, i0, q, all);
+            PHASE_END_T(P_C);
+            // ---- phase D
+            if (g0.n) run_phase_d<S>(sc, g0, 0, all);
+            if (g1.n) run_phase_d<H>(sc, g1, i0, all);
+            PHASE_END_T(P_D_TRIAL);
         }
-        {   // four-TU candidates: sub-TU k of a chunk of modes, each with its own reconstruction as neighbour
-            const int m0 = chunk * P::N1, n = (S == 16 && r >= 4) ? 0 : imax(0, imin(P::N1, NMODE - m0));
-            g1.n = n; g1.cand0 = NMODE + m0; g1.mode0 = m0; g1.ty = y0 + (k >> 1) * H; g1.tx = x0 + (k & 1) * H; g1.av = sub_avail(av, k); g1.priv = 1;
-            g1.cuy = y0; g1.cux = x0; g1.cus = S; g1.tu = k; g1.one_tu = 0; g1.grec = 1;
-            g1.blk = P::BLK1; g1.pred = P::PRED1; g1.psum = P::PSUM1; g1.bord = P::BORD1;
-            g1.rec = P::REC1; g1.rec_stride = 4 * H; g1.rec_pitch = 0;
-        }
-        g2.n = 0;
-        if (S == 8) {   // NxN PU k: all 35 modes, neighbours from the window (earlier PUs' winners are already there)
-            g2.n = 35; g2.cand0 = 2 * NMODE; g2.mode0 = 0; g2.ty = y0 + (k >> 1) * 4; g2.tx = x0 + (k & 1) * 4; g2.av = sub_avail(av, k); g2.priv = 0;
-            g2.cuy = g2.ty; g2.cux = g2.tx; g2.cus = 4; g2.tu = 0; g2.one_tu = 0; g2.grec = 0;
-            g2.blk = P::BLK2; g2.pred = P::PRED2; g2.psum = P::PSUM2; g2.bord = P::BORD2;
-            g2.rec = P::REC2; g2.rec_stride = 16; g2.rec_pitch = 4;
-        }
-        const int i0 = g0.n * S, i1 = g1.n * H;
-        // ---- phase 0: reference samples
-        run_borders<S>(g0, 0);
-        run_borders<H>(g1, 4 * S + 1);
-        if (S == 8) run_borders<4>(g2, 4 * S + 1 + 4 * H + 1);
-        PHASE_END_T(P_BORDER);
-        // ---- phase A
-        if (g0.n) run_phase_a<S>(g0, 0);
-        if (g1.n) run_phase_a<H>(g1, i0);
-        if (S == 8) run_phase_a<4>(g2, i0 + i1);
-        PHASE_END_T(P_A);
-        // ---- phase B
-        if (g0.n) run_phase_b<S>(g0, 0, q);
-        if (g1.n) run_phase_b<H>(g1, i0, q);
-        if (S == 8) run_phase_b<4>(g2, i0 + i1, q);
-        PHASE_END_T(P_B);
-        // ---- phase C
-        if (g0.n) run_phase_c<S>(sc, g0, 0, q);
-        if (g1.n) run_phase_c<H>(sc, g1, i0, q);
-        if (S == 8) run_phase_c<4>(sc, g2, i0 + i1, q);
-        PHASE_END_T(P_C);
-        // ---- phase D (+ the trial coders that only need the levels of phase C)
-        constexpr int ND = S == 8 ? NT / 2 : NT;   // 8x8 nodes: the upper half of every picture's threads hosts NxN PU coders
-        if (S == 8) {   // NxN PU coders of this round, all pictures of the gang, packed into full warps
-            GANG_FOR_UPPER(u, GANG_RT * NMODE) {
-                const int pic = u / NMODE, m = u - pic * NMODE;
-                trial_lane<S>(gang_sm(pic), pic, 2 * NMODE + m, depth, y0, x0);
+    } else {
+        // 8x8 nodes: two independent chains.  Team A (lower half of every picture's threads) evaluates the one-TU and
+        // four-TU candidates; team B (upper half) walks the four NxN PUs, whose CABAC lanes are the long pole.  Team A
+        // reads the window outside the CU only and team B writes it inside the CU only, so the chains meet at the end.
+        TEAM_A {
+            const Team ta = {0, NT / 2};
+            for (int r = 0; r < 4; r++) {
+                const Grp g0 = group0(r), g1 = group1(r);
+                const int i0 = g0.n * S;
+                run_borders<S>(g0, 0, ta);
+                run_borders<H>(g1, 4 * S + 1, ta);
+                TEAM_SYNC(1);
+                if (g0.n) run_phase_a<S>(g0, 0, ta);
+                run_phase_a<H>(g1, i0, ta);
+                TEAM_SYNC(1);
+                if (g0.n) run_phase_b<S>(g0, 0, q, ta);
+                run_phase_b<H>(g1, i0, q, ta);
+                TEAM_SYNC(1);
+                if (g0.n) run_phase_c<S>(sc, g0, 0, q, ta);
+                run_phase_c<H>(sc, g1, i0, q, ta);
+                TEAM_SYNC(1);
+                if (g0.n) run_phase_d<S>(sc, g0, 0, ta);
+                run_phase_d<H>(sc, g1, i0, ta);
+                TEAM_SYNC(1);
             }
         }
-        if (g0.n) run_phase_d<S>(sc, g0, 0, ND);
-        if (g1.n) run_phase_d<H>(sc, g1, i0, ND);
-        if (S == 8) run_phase_d<4>(sc, g2, i0 + i1, ND);
+        TEAM_B {
+            const Team tb = {NT / 2, NT / 2};
+            for (int k = 0; k < 4; k++) {
+                const Grp g2 = group2(k);
+                run_borders<4>(g2, 0, tb);
+                TEAM_SYNC(2);
+                run_phase_a<4>(g2, 0, tb);
+                TEAM_SYNC(2);
+                run_phase_b<4>(g2, 0, q, tb);
+                TEAM_SYNC(2);
+                run_phase_c<4>(sc, g2, 0, q, tb);
+                TEAM_SYNC(2);
+                run_phase_d<4>(sc, g2, 0, tb);
+                // NxN PU coders of this PU, all pictures of the gang, packed into full warps
+                GANG_FOR_UPPER(u, GANG_RT * NMODE) {
+                    const int pic = u / NMODE, m = u - pic * NMODE;
+                    trial_lane<S>(gang_sm(pic), pic, 2 * NMODE + m, depth, y0, x0);
+                }
+                TEAM_SYNC(2);
+                PAR_FOR_TEAM(one, 1, NT / 2, NT / 2, 0) {   // best PU mode, last minimum wins (HEVCe.c:1521)
+                    int best = IMAX, bm = 0;
+                    for (int m = 0; m < NMODE; m++) {
+                        const int c = rd_cost(rk, sm.cand_sse[2 * NMODE + m], sm.cand_bits[2 * NMODE + m]);
+                        if (best >= c) { best = c; bm = m; }
+                    }
+                    const int ci = 2 * NMODE + bm;
+                    sm.nxn_pm[k] = bm;
+                    sm.nxn_nz[k] = sm.cgnz[ci][0];
+                    const s16* lp = sc.glev + (size_t)ci * LEV_STRIDE;
+                    for (int i = 0; i < 16; i++) {
+                        sm.nxn_lev[k][i] = lp[i];
+                        HEVCE_WIN(sm, g2.ty + (i >> 2), g2.tx + (i & 3)) = sm.pool[g2.rec + bm * 16 + i];
+                    }
+                }
+                TEAM_SYNC(2);
+            }
+        }
         PHASE_END_T(P_D_TRIAL);
-        if (S == 8) {
-            PAR_FOR(one, 1) {   // best PU mode, last minimum wins (HEVCe.c:1521)
-                int best = IMAX, bm = 0;
-                for (int m = 0; m < NMODE; m++) {
-                    const int c = rd_cost(rk, sm.cand_sse[2 * NMODE + m], sm.cand_bits[2 * NMODE + m]);
-                    if (best >= c) { best = c; bm = m; }
-                }
-                const int ci = 2 * NMODE + bm;
-                sm.nxn_pm[k] = bm;
-                sm.nxn_nz[k] = sm.cgnz[ci][0];
-                const s16* lp = sc.glev + (size_t)ci * LEV_STRIDE;
-                for (int i = 0; i < 16; i++) {
-                    sm.nxn_lev[k][i] = lp[i];
-                    HEVCE_WIN(sm, g2.ty + (i >> 2), g2.tx + (i & 3)) = sm.pool[g2.rec + bm * 16 + i];
-                }
-            }
-            PHASE_END_T(P_PU_ARGMIN);
-        }
     }
 
     // ---- all one-TU / four-TU trial coders of the gang (70 per picture), packed step-major into full warps; for 8x8
