@@ -390,6 +390,22 @@ struct CtuRec {          // what the commit pass needs for one CTU (written by t
     u8 kind[16];
 };
 
+// Decisions of one picture as raster maps (host side; hevce_session_partition and the simulator): CU size and luma
+// intra mode per 4x4 unit, CU kind per 8x8 unit (0: one TU, 1: four TUs, 2: NxN)
+inline void unpack_partition(const CtuRec* recs, int H, int W, u8* cu_size, u8* mode, u8* kind) {
+    const int cw = W / CTU, w4 = W / 4, w8 = W / 8;
+    for (int c = 0; c < (H / CTU) * cw; c++) {
+        const CtuRec& r = recs[c];
+        const int y4 = (c / cw) * 8, x4 = (c % cw) * 8;
+        for (int i = 0; i < 64; i++) {
+            if (cu_size) cu_size[(size_t)(y4 + i / 8) * w4 + x4 + i % 8] = r.msz[(1 + i / 8) * 9 + 1 + i % 8];
+            if (mode) mode[(size_t)(y4 + i / 8) * w4 + x4 + i % 8] = r.mpm[(1 + i / 8) * 9 + 1 + i % 8];
+        }
+        if (kind)
+            for (int i = 0; i < 16; i++) kind[(size_t)(y4 / 2 + i / 4) * w8 + x4 / 2 + i % 4] = r.kind[i];
+    }
+}
+
 struct Job {
     CtuRec* recs;      // one record per CTU, raster order
     s16* levs;         // CTU*CTU final levels per CTU: CUs at their z-order offset, group-blocked
@@ -404,7 +420,7 @@ struct Job {
 };
 
 enum { ERR_OVERFLOW = 1, ERR_COMMIT_MISMATCH = 2 };
-enum { P_BORDER, P_A, P_B, P_C, P_D_TRIAL, P_PU_ARGMIN, P_TRIAL, P_DECIDE, P_ADOPT, P_ENTER, P_LOAD, P_COMMIT, P_MISC, P_NTAGS };
+enum { P_BORDER, P_A, P_B, P_C, P_D_TRIAL, P_PU_ARGMIN, P_TRIAL, P_DECIDE, P_ADOPT, P_ENTER, P_LOAD, P_COMMIT, P_MISC, P_TA, P_TB_PIX, P_TB_CABAC, P_TB_ARGMIN, P_NTAGS };
 
 constexpr int LEV_STRIDE = CTU * CTU;   // per-candidate level store (all TUs of the candidate)
 constexpr int NREC = 70;                // candidates whose reconstruction is kept (one-TU + four-TU)
@@ -489,14 +505,21 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 #define GANG_RT GANG
 #define GANG_FOR(L, n) for (int L = (int)threadIdx.x; L < (n); L += NT * GANG)
 #define GANG_FOR_UPPER(u, n) for (int u = HEVCE_TID >= NT / 2 ? (int)(threadIdx.x / NT) * (NT / 2) + HEVCE_TID - NT / 2 : (n); u < (n); u += GANG * NT / 2)
+// the upper-half threads that GANG_FOR_UPPER(u, first) leaves idle share n items of any picture of the gang
+#define GANG_FOR_UPPER_FREE(it, first, n) for (int it = (HEVCE_TID >= NT / 2 && (int)(threadIdx.x / NT) * (NT / 2) + HEVCE_TID - NT / 2 >= (first)) ? (int)(threadIdx.x / NT) * (NT / 2) + HEVCE_TID - NT / 2 - (first) : (n); it < (n); it += GANG * NT / 2 - (first))
 #define PHASE_END() __syncthreads()
 #if defined(HEVCE_PROFILE)   // per-phase latency histogram (development builds only)
-extern __device__ unsigned long long g_phase_cycles[16];
-extern __device__ unsigned long long g_phase_count[16];
+extern __device__ unsigned long long g_phase_cycles[24];
+extern __device__ unsigned long long g_phase_count[24];
 #define PHASE_END_T(tag) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_ = clock64(); \
     atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - sm.prof_last)); atomicAdd(&g_phase_count[tag], 1ull); sm.prof_last = t_; } } while (0)
+#define TEAM_PROF_BEGIN() long long tp_ = clock64()
+#define TEAM_PROF(tag, lead) do { if (threadIdx.x == (lead)) { const long long t_ = clock64(); \
+    atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - tp_)); atomicAdd(&g_phase_count[tag], 1ull); tp_ = t_; } } while (0)
 #else
 #define PHASE_END_T(tag) __syncthreads()
+#define TEAM_PROF_BEGIN() ((void)0)
+#define TEAM_PROF(tag, lead) ((void)0)
 #endif
 #define HEVCE_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define HEVCE_ATOMIC_ADD(p, v) atomicAdd((p), (v))
@@ -519,8 +542,11 @@ inline int sim_item(int i, int n) {
 #define GANG_RT 1
 #define GANG_FOR(L, n) PAR_FOR(L, n)
 #define GANG_FOR_UPPER(u, n) PAR_FOR(u, n)
+#define GANG_FOR_UPPER_FREE(it, first, n) PAR_FOR(it, n)
 #define PHASE_END() ((void)0)
 #define PHASE_END_T(tag) ((void)0)
+#define TEAM_PROF_BEGIN() ((void)0)
+#define TEAM_PROF(tag, lead) ((void)0)
 #define HEVCE_ATOMIC_OR(p, v) (*(p) |= (v))
 #define HEVCE_ATOMIC_ADD(p, v) (*(p) += (v))
 #endif
@@ -1160,6 +1186,18 @@ HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, 
     const Scratch sc = scref;
     PAR_FOR_TEAM(item, g.n * T, tm.t0, tm.nthr, off) phase_d_item<T>(sm, sc, g, item);
 }
+// phase D of a group for every picture of the gang, on the upper-half threads that host no trial lane
+template <int T>
+HEVCE_HD HEVCE_NOINLINE void run_phase_d_free(const Grp& gref, int first) {
+    const Grp g = gref;
+    const int per = g.n * T;
+    GANG_FOR_UPPER_FREE(it, first, GANG_RT * per) {
+        const int pic = it / per;
+        Shared& ps = gang_sm(pic);
+        const Scratch sc = ps.sc;
+        phase_d_item<T>(ps, sc, g, it - pic * per);
+    }
+}
 
 // shared-memory carve-up of the pool for a node of size S: group 0 = one-TU candidates (T = S), group 1 = four-TU
 // candidates (T = S/2), group 2 (S = 8 only) = NxN PU candidates (T = 4)
@@ -1347,6 +1385,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         // reads the window outside the CU only and team B writes it inside the CU only, so the chains meet at the end.
         TEAM_A {
             const Team ta = {0, NT / 2};
+            TEAM_PROF_BEGIN();
             for (int r = 0; r < 4; r++) {
                 const Grp g0 = group0(r), g1 = group1(r);
                 const int i0 = g0.n * S;
@@ -1365,10 +1404,12 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
                 if (g0.n) run_phase_d<S>(sc, g0, 0, ta);
                 run_phase_d<H>(sc, g1, i0, ta);
                 TEAM_SYNC(1);
+                TEAM_PROF(P_TA, 0);
             }
         }
         TEAM_B {
             const Team tb = {NT / 2, NT / 2};
+            TEAM_PROF_BEGIN();
             for (int k = 0; k < 4; k++) {
                 const Grp g2 = group2(k);
                 run_borders<4>(g2, 0, tb);
@@ -1379,29 +1420,31 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
                 TEAM_SYNC(2);
                 run_phase_c<4>(sc, g2, 0, q, tb);
                 TEAM_SYNC(2);
-                run_phase_d<4>(sc, g2, 0, tb);
-                // NxN PU coders of this PU, all pictures of the gang, packed into full warps
+                TEAM_PROF(P_TB_PIX, NT / 2);
+                // NxN PU coders of this PU, all pictures of the gang, packed into full warps; the threads left over
+                // reconstruct the candidates meanwhile (phase D of any picture of the gang)
                 GANG_FOR_UPPER(u, GANG_RT * NMODE) {
                     const int pic = u / NMODE, m = u - pic * NMODE;
                     trial_lane<S>(gang_sm(pic), pic, 2 * NMODE + m, depth, y0, x0);
                 }
+                run_phase_d_free<4>(g2, GANG_RT * NMODE);
                 TEAM_SYNC(2);
-                PAR_FOR_TEAM(one, 1, NT / 2, NT / 2, 0) {   // best PU mode, last minimum wins (HEVCe.c:1521)
+                TEAM_PROF(P_TB_CABAC, NT / 2);
+                PAR_FOR_TEAM(m, NMODE, NT / 2, NT / 2, 0) sm.cand_bits[2 * NMODE + m] = rd_cost(rk, sm.cand_sse[2 * NMODE + m], sm.cand_bits[2 * NMODE + m]);
+                TEAM_SYNC(2);
+                PAR_FOR_TEAM(i, 16, NT / 2, NT / 2, 0) {   // best PU mode, last minimum wins (HEVCe.c:1521); one sample per thread
                     int best = IMAX, bm = 0;
                     for (int m = 0; m < NMODE; m++) {
-                        const int c = rd_cost(rk, sm.cand_sse[2 * NMODE + m], sm.cand_bits[2 * NMODE + m]);
+                        const int c = sm.cand_bits[2 * NMODE + m];
                         if (best >= c) { best = c; bm = m; }
                     }
                     const int ci = 2 * NMODE + bm;
-                    sm.nxn_pm[k] = bm;
-                    sm.nxn_nz[k] = sm.cgnz[ci][0];
-                    const s16* lp = sc.glev + (size_t)ci * LEV_STRIDE;
-                    for (int i = 0; i < 16; i++) {
-                        sm.nxn_lev[k][i] = lp[i];
-                        HEVCE_WIN(sm, g2.ty + (i >> 2), g2.tx + (i & 3)) = sm.pool[g2.rec + bm * 16 + i];
-                    }
+                    if (i == 0) { sm.nxn_pm[k] = bm; sm.nxn_nz[k] = sm.cgnz[ci][0]; }
+                    sm.nxn_lev[k][i] = sc.glev[(size_t)ci * LEV_STRIDE + i];
+                    HEVCE_WIN(sm, g2.ty + (i >> 2), g2.tx + (i & 3)) = sm.pool[g2.rec + bm * 16 + i];
                 }
                 TEAM_SYNC(2);
+                TEAM_PROF(P_TB_ARGMIN, NT / 2);
             }
         }
         PHASE_END_T(P_D_TRIAL);

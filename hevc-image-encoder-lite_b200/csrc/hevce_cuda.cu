@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -37,8 +38,8 @@ using namespace hevce;
 __device__ Tables g_tables;
 #if defined(HEVCE_PROFILE)
 namespace hevce {
-__device__ unsigned long long g_phase_cycles[16];
-__device__ unsigned long long g_phase_count[16];
+__device__ unsigned long long g_phase_cycles[24];
+__device__ unsigned long long g_phase_count[24];
 }
 #endif
 
@@ -70,6 +71,31 @@ __global__ void __launch_bounds__(NT) hevce_commit_kernel(const Job* __restrict_
     const Job job = jobs[blockIdx.y];
     const int nctu = (job.H / CTU) * (job.W / CTU), ctu = blockIdx.x * NT + threadIdx.x;
     if (ctu < nctu) commit_ctu(job, ctu, threadIdx.x);
+}
+
+// Quality pass (HEVCeMain.c:116-133): sum of squared differences between source and reconstruction over the area both
+// cover.  blockIdx.y = picture, a CTA strides over 16-pixel segments of the reconstruction rows.  HBM-bound: 2 B/pixel.
+__global__ void __launch_bounds__(256) hevce_quality_kernel(const Job* __restrict__ jobs, unsigned long long* __restrict__ sse) {
+    const Job job = jobs[blockIdx.y];
+    const int hm = min(job.src_h, job.H), wm = min(job.src_w, job.W), segs = (wm + 15) / 16;
+    unsigned long long acc = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)hm * segs; t += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(t / segs), x0 = (int)(t % segs) * 16;
+        const uint4 rv = *(const uint4*)(job.rcon + (size_t)y * job.W + x0);   // rows of the reconstruction are 32-byte aligned
+        const u32 rw[4] = {rv.x, rv.y, rv.z, rv.w};
+        const u8* ip = job.img + (size_t)y * job.src_w + x0;
+        unsigned part = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (x0 + k < wm) {
+                const int d = (int)ip[k] - (int)((rw[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                part += (unsigned)(d * d);
+            }
+        }
+        acc += part;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sse + blockIdx.y, acc);
 }
 
 // integer-issue micro-benchmark: 8 independent IMAD chains + 8 independent LOP3/IADD3 chains per thread
@@ -163,6 +189,8 @@ struct hevce_session {
     s16 *d_glev = nullptr, *d_lev = nullptr; u8 *d_grec = nullptr, *d_line = nullptr;
     size_t c_glev = 0, c_lev = 0, c_grec = 0, c_line = 0;
     CtuRec* d_recs = nullptr; size_t c_recs = 0;
+    unsigned long long* d_sse = nullptr; size_t c_sse = 0;
+    float quality_ms = 0.f;
     std::vector<size_t> ctu_off;
     int line_pitch = 0;
     // pinned staging
@@ -363,6 +391,50 @@ extern "C" int hevce_session_download(hevce_session* s, unsigned char* const* pb
     return status;
 }
 
+// f3: per-picture MSE / PSNR of the last encode, reduced on the device (calcImagePSNR, HEVCeMain.c:116-133)
+extern "C" int hevce_session_quality(hevce_session* s, double* mse, double* psnr) {
+    if (!s || (s->n > 0 && !mse && !psnr)) return HEVCE_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    if (s->n == 0) return 0;
+    int rc = grow(&s->d_sse, &s->c_sse, (size_t)s->n);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(s->d_sse, 0, (size_t)s->n * sizeof(unsigned long long), s->stream));
+    long long maxpix = 0;
+    for (const Job& j : s->jobs) maxpix = std::max(maxpix, (long long)j.H * j.W);
+    const dim3 grid((unsigned)std::max(1LL, std::min(1024LL, (maxpix / 16 + 255) / 256)), (unsigned)s->n);
+    CK(cudaEventRecord(s->ev0, s->stream));
+    hevce_quality_kernel<<<grid, 256, 0, s->stream>>>(s->d_jobs, s->d_sse);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->ev1, s->stream));
+    std::vector<unsigned long long> sse((size_t)s->n);
+    CK(cudaMemcpyAsync(sse.data(), s->d_sse, sse.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaEventElapsedTime(&s->quality_ms, s->ev0, s->ev1));
+    s->launches += 1;
+    for (int i = 0; i < s->n; i++) {
+        const Job& j = s->jobs[i];
+        double m = (double)sse[i] / std::min(j.src_h, j.H) / std::min(j.src_w, j.W);
+        if (m < 1e-9) m = 1e-9;
+        if (mse) mse[i] = m;
+        if (psnr) psnr[i] = 10.0 * log10(255 * 255 / m);
+    }
+    return 0;
+}
+extern "C" float hevce_session_quality_ms(const hevce_session* s) { return s ? s->quality_ms : 0.f; }
+
+// Decisions of picture i after hevce_session_encode: CU size and luma intra mode per 4x4 unit ((H/4)*(W/4) bytes each),
+// CU kind per 8x8 unit ((H/8)*(W/8) bytes: 0 one TU, 1 four TUs, 2 NxN).  Any pointer may be NULL.
+extern "C" int hevce_session_partition(hevce_session* s, int i, unsigned char* cu_size, unsigned char* mode, unsigned char* kind) {
+    if (!s || i < 0 || i >= s->n) return HEVCE_ERR_ARG;
+    CK(cudaSetDevice(s->device));
+    const Job& j = s->jobs[i];
+    std::vector<CtuRec> recs((size_t)(j.H / CTU) * (j.W / CTU));
+    CK(cudaMemcpyAsync(recs.data(), s->d_recs + s->ctu_off[i], recs.size() * sizeof(CtuRec), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    unpack_partition(recs.data(), j.H, j.W, cu_size, mode, kind);
+    return 0;
+}
+
 extern "C" float hevce_session_kernel_ms(const hevce_session* s) { return s ? s->kernel_ms : 0.f; }
 extern "C" float hevce_session_commit_ms(const hevce_session* s) { return s ? s->commit_ms : 0.f; }
 extern "C" int hevce_session_launches(const hevce_session* s) { return s ? s->launches : 0; }
@@ -380,7 +452,7 @@ extern "C" void hevce_session_destroy(hevce_session* s) {
     cudaSetDevice(s->device);
     cudaFree(s->d_img); cudaFree(s->d_rcon); cudaFree(s->d_out); cudaFree(s->d_jobs); cudaFree(s->d_order);
     cudaFree(s->d_results); cudaFree(s->d_counter); cudaFree(s->d_slots); cudaFree(s->d_glev); cudaFree(s->d_grec);
-    cudaFree(s->d_lev); cudaFree(s->d_line); cudaFree(s->d_recs);
+    cudaFree(s->d_lev); cudaFree(s->d_line); cudaFree(s->d_recs); cudaFree(s->d_sse);
     if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -391,12 +463,12 @@ extern "C" void hevce_session_destroy(hevce_session* s) {
 
 #if defined(HEVCE_PROFILE)
 extern "C" __attribute__((visibility("default"))) void hevce_profile_dump(void) {
-    unsigned long long c[16], n[16];
+    unsigned long long c[24], n[24];
     cudaMemcpyFromSymbol(c, g_phase_cycles, sizeof c);
     cudaMemcpyFromSymbol(n, g_phase_count, sizeof n);
-    static const char* names[] = {"border", "A", "B", "C", "D+pu/trial", "pu_argmin", "trial(S>8)", "decide", "adopt", "enter", "load", "commit", "misc"};
+    static const char* names[] = {"border", "A", "B", "C", "D+pu/trial", "pu_argmin", "trial(S>8)", "decide", "adopt", "enter", "load", "commit", "misc", "teamA/round", "teamB pixel", "teamB d+cabac", "teamB argmin"};
     unsigned long long tot = 0;
-    for (int i = 0; i < P_NTAGS; i++) tot += c[i];
+    for (int i = 0; i < P_TA; i++) tot += c[i];   // team tags overlap "D+pu/trial" of the 8x8 nodes
     for (int i = 0; i < P_NTAGS; i++)
         printf("phase %-12s count %10llu cycles %14llu  %5.1f%%  avg %8.0f\n", names[i], n[i], c[i], 100.0 * c[i] / (double)tot, n[i] ? (double)c[i] / n[i] : 0.0);
 }

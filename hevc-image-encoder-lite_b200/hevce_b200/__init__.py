@@ -24,6 +24,7 @@ EXPORTS = [
     "hevce_measure_int_peak", "hevce_session_create", "hevce_session_upload", "hevce_session_encode",
     "hevce_session_download", "hevce_session_kernel_ms", "hevce_session_commit_ms", "hevce_session_launches", "hevce_session_grid",
     "hevce_session_h2d_bytes", "hevce_session_d2h_bytes", "hevce_session_destroy",
+    "hevce_session_quality", "hevce_session_quality_ms", "hevce_session_partition",
 ]
 
 
@@ -64,7 +65,11 @@ def lib():
         L.hevce_session_encode.argtypes = [ctypes.c_void_p]
         L.hevce_session_download.restype = ctypes.c_int
         L.hevce_session_download.argtypes = [ctypes.c_void_p, ctypes.POINTER(_u8p), ctypes.POINTER(_u8p), _ip]
-        for f in ("hevce_session_kernel_ms", "hevce_session_commit_ms"):
+        L.hevce_session_quality.restype = ctypes.c_int
+        L.hevce_session_quality.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.hevce_session_partition.restype = ctypes.c_int
+        L.hevce_session_partition.argtypes = [ctypes.c_void_p, ctypes.c_int, _u8p, _u8p, _u8p]
+        for f in ("hevce_session_kernel_ms", "hevce_session_commit_ms", "hevce_session_quality_ms"):
             getattr(L, f).restype = ctypes.c_float
             getattr(L, f).argtypes = [ctypes.c_void_p]
         for f in ("hevce_session_launches", "hevce_session_grid"):
@@ -189,6 +194,28 @@ class Session:
         if rc < 0:
             raise HevceError(rc, "hevce_session_download")
         return [outs[i][: lens[i]].tobytes() for i in range(self.n)], rcons
+
+    def quality(self):
+        """(mse, psnr) of every picture of the last encode, reduced on the device (calcImagePSNR, HEVCeMain.c:116-133)."""
+        mse, psnr = np.zeros(self.n, np.float64), np.zeros(self.n, np.float64)
+        dp = ctypes.POINTER(ctypes.c_double)
+        rc = lib().hevce_session_quality(self._h, mse.ctypes.data_as(dp), psnr.ctypes.data_as(dp))
+        if rc < 0:
+            raise HevceError(rc, "hevce_session_quality")
+        return mse, psnr
+
+    @property
+    def quality_ms(self):
+        return lib().hevce_session_quality_ms(self._h)
+
+    def partition(self, i):
+        """Decisions of picture i: (cu_size, mode) per 4x4 unit and kind per 8x8 unit (0 one TU, 1 four TUs, 2 NxN)."""
+        h, w = padded(self.shapes[i][0], self.max_dim), padded(self.shapes[i][1], self.max_dim)
+        cu, mode, kind = np.zeros((h // 4, w // 4), np.uint8), np.zeros((h // 4, w // 4), np.uint8), np.zeros((h // 8, w // 8), np.uint8)
+        rc = lib().hevce_session_partition(self._h, int(i), cu.ctypes.data_as(_u8p), mode.ctypes.data_as(_u8p), kind.ctypes.data_as(_u8p))
+        if rc < 0:
+            raise HevceError(rc, "hevce_session_partition")
+        return cu, mode, kind
 
     @property
     def launches(self):

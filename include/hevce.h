@@ -74,6 +74,15 @@ HEVCE_API float hevce_session_kernel_ms(const hevce_session *s);   /* CUDA-event
 HEVCE_API float hevce_session_commit_ms(const hevce_session *s);   /* ... of the hevce_commit_kernel launch that follows it */
 HEVCE_API int  hevce_session_launches(const hevce_session *s);     /* kernel launches issued so far by this session */
 HEVCE_API int  hevce_session_grid(const hevce_session *s);         /* CTAs of the persistent encode grid */
+/* Per-picture quality of the last encode, reduced on the device: mean squared error and PSNR between source and
+ * reconstruction over the area both cover, MSE floored at 1e-9 (calcImagePSNR, HEVCeMain.c:116-133, printed by the
+ * reference CLI at HEVCeMain.c:201-212).  mse / psnr: n doubles each, either may be NULL. */
+HEVCE_API int  hevce_session_quality(hevce_session *s, double *mse, double *psnr);
+HEVCE_API float hevce_session_quality_ms(const hevce_session *s);  /* CUDA-event duration of the last hevce_quality_kernel launch */
+/* Decisions of picture i of the last encode as raster maps: CU size (8/16/32) and luma intra mode (0..34) per 4x4 unit,
+ * (H/4)*(W/4) bytes each; CU kind per 8x8 unit, (H/8)*(W/8) bytes: 0 = one TU, 1 = four TUs, 2 = NxN (what the
+ * reference keeps in map_cu_sz_0 / map_pmode_0, HEVCe.c:1591-1592, plus the transform split).  Any pointer may be NULL. */
+HEVCE_API int  hevce_session_partition(hevce_session *s, int i, unsigned char *cu_size, unsigned char *mode, unsigned char *kind);
 HEVCE_API long long hevce_session_h2d_bytes(const hevce_session *s);
 HEVCE_API long long hevce_session_d2h_bytes(const hevce_session *s);
 HEVCE_API void hevce_session_destroy(hevce_session *s);

@@ -10,6 +10,9 @@
 
 namespace hevce { int g_sim_order = 0; Shared* g_sim_sm = nullptr; Tables* g_sim_tb = nullptr; CommitShared* g_sim_csm = nullptr; }
 
+static std::vector<hevce::CtuRec> g_last_recs;
+static int g_last_h = 0, g_last_w = 0;
+
 extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned char* img, unsigned char* rcon,
                                 int* ysz, int* xsz, int q, int order, int max_dim, int* err) {
     using namespace hevce;
@@ -44,8 +47,14 @@ extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned 
     for (int c = 0; c < nctu; c++) commit_ctu(job, order == 1 ? nctu - 1 - c : c, (c * 7) % NT);
     delete cs;
     *ysz = job.H; *xsz = job.W;
+    g_last_recs = recs; g_last_h = job.H; g_last_w = job.W;
     if (err) *err = result[1];
     return result[0];
+}
+
+// decisions of the last hevce_sim_encode call: (H/4)x(W/4) CU sizes and modes, (H/8)x(W/8) CU kinds
+extern "C" void hevce_sim_last_partition(unsigned char* cu_size, unsigned char* mode, unsigned char* kind) {
+    hevce::unpack_partition(g_last_recs.data(), g_last_h, g_last_w, cu_size, mode, kind);
 }
 
 extern "C" int hevce_sim_shared_bytes() { return (int)sizeof(hevce::Shared); }

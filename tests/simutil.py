@@ -43,3 +43,11 @@ def sim_encode(img, q, order=0, max_dim=8192):
                                ctypes.byref(ys), ctypes.byref(xs), int(q), int(order), int(max_dim), ctypes.byref(err))
     assert (ys.value, xs.value) == (hp, wp)
     return out[:n].tobytes(), rcon, err.value
+
+
+def sim_last_partition(shape):
+    """(cu_size, mode, kind) maps of the last sim_encode call; shape = padded picture shape."""
+    hp, wp = shape
+    cu, mode, kind = np.zeros((hp // 4, wp // 4), np.uint8), np.zeros((hp // 4, wp // 4), np.uint8), np.zeros((hp // 8, wp // 8), np.uint8)
+    sim().hevce_sim_last_partition(cu.ctypes.data_as(_u8p), mode.ctypes.data_as(_u8p), kind.ctypes.data_as(_u8p))
+    return cu, mode, kind
