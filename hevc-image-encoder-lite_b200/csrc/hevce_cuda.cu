@@ -45,7 +45,7 @@ __device__ unsigned long long g_phase_count[24];
 
 // A CTA = GANG pictures of identical padded size, one per group of NT threads.  `gangs` lists GANG job indices per
 // work unit (a short gang repeats its first job: the duplicate writes identical bytes).
-__global__ void __launch_bounds__(NT * GANG, 1)
+__global__ void __launch_bounds__(NT * GANG, (6 % GANG == 0) ? 6 / GANG : 1)
 hevce_encode_kernel(const Job* __restrict__ jobs, const int* __restrict__ gangs, int ngangs, const Scratch* __restrict__ slots, int* counter) {
     const int member = threadIdx.x / NT;
     Shared& sm = my_sm();
