@@ -105,3 +105,28 @@ def test_decoder_equals_deblocked_reconstruction(H, q):
             pytest.skip("no HEVC decoder in this OpenCV build")
         cu, mode, kind = parts[i]
         assert np.array_equal(luma, D.deblock(r, cu, kind, q)), (i, q)
+
+
+def test_quality_study_on_the_batch_api(H, tmp_path):
+    """f4: tools/hevc_eval.py on three Kodak crops; the HEVC column must be the batch encoder's bytes and, as the
+    reference's README reports for the full set, HEVC needs fewer bits than JPEG at equal SSIM."""
+    pytest.importorskip("PIL.Image")
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import hevc_eval as E
+    from PIL import Image
+    K = WL.kodak_landscape()
+    src = tmp_path / "in"
+    src.mkdir()
+    crops = [K[3][64:64 + 250, 100:100 + 375], K[14][:256, :384], K[20][200:456, 300:684]]
+    for i, c in enumerate(crops):
+        Image.fromarray(c).save(src / f"p{i}.png")
+    rows, means = E.evaluate(str(src), str(tmp_path / "out"), 3, formats=E.COMPARISONS[:1] + E.COMPARISONS[2:], log=lambda *_: None)
+    assert [r["name"] for r in rows] == ["p0.png", "p1.png", "p2.png"]
+    for r, c in zip(rows, crops):
+        s, rc = H.HEVCImageEncoder(E.image_pad(c), 3)
+        base = str(tmp_path / "out" / os.path.splitext(r["name"])[0])
+        assert open(base + ".h265", "rb").read() == s
+        assert r["HEVC"][1] == pytest.approx(8.0 * len(s) / rc.size)
+        assert abs(r["JPEG"][0] - r["HEVC"][0]) < 0.02 and os.path.exists(base + ".jpg") and os.path.exists(base + ".webp")
+    assert means["JPEG"] > means["HEVC"]
