@@ -508,6 +508,9 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 // the upper-half threads that GANG_FOR_UPPER(u, first) leaves idle share n items of any picture of the gang
 #define GANG_FOR_UPPER_FREE(it, first, n) for (int it = (HEVCE_TID >= NT / 2 && (int)(threadIdx.x / NT) * (NT / 2) + HEVCE_TID - NT / 2 >= (first)) ? (int)(threadIdx.x / NT) * (NT / 2) + HEVCE_TID - NT / 2 - (first) : (n); it < (n); it += GANG * NT / 2 - (first))
 #define PHASE_END() __syncthreads()
+// between the pixel phases A..D of one round: all lines of a candidate's TU are work items of the same warp (T <= 32
+// consecutive items, groups start at multiples of T), so the hand-over needs no CTA- or team-wide barrier
+#define WARP_SYNC() __syncwarp()
 #if defined(HEVCE_PROFILE)   // per-phase latency histogram (development builds only)
 extern __device__ unsigned long long g_phase_cycles[24];
 extern __device__ unsigned long long g_phase_count[24];
@@ -544,6 +547,7 @@ inline int sim_item(int i, int n) {
 #define GANG_FOR_UPPER(u, n) PAR_FOR(u, n)
 #define GANG_FOR_UPPER_FREE(it, first, n) PAR_FOR(it, n)
 #define PHASE_END() ((void)0)
+#define WARP_SYNC() ((void)0)
 #define PHASE_END_T(tag) ((void)0)
 #define TEAM_PROF_BEGIN() ((void)0)
 #define TEAM_PROF(tag, lead) ((void)0)
@@ -1362,19 +1366,16 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             run_borders<S>(g0, 0, all);
             run_borders<H>(g1, 4 * S + 1, all);
             PHASE_END_T(P_BORDER);
-            // ---- phase A
+            // ---- phases A..D: warp-local hand-over (see WARP_SYNC)
             if (g0.n) run_phase_a<S>(g0, 0, all);
             if (g1.n) run_phase_a<H>(g1, i0, all);
-            PHASE_END_T(P_A);
-            // ---- phase B
+            WARP_SYNC();
             if (g0.n) run_phase_b<S>(g0, 0, q, all);
             if (g1.n) run_phase_b<H>(g1, i0, q, all);
-            PHASE_END_T(P_B);
-            // ---- phase C
+            WARP_SYNC();
             if (g0.n) run_phase_c<S>(sc, g0, 0, q, all);
             if (g1.n) run_phase_c<H>(sc, g1, i0, q, all);
-            PHASE_END_T(P_C);
-            // ---- phase D
+            WARP_SYNC();
             if (g0.n) run_phase_d<S>(sc, g0, 0, all);
             if (g1.n) run_phase_d<H>(sc, g1, i0, all);
             PHASE_END_T(P_D_TRIAL);
@@ -1394,13 +1395,13 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
                 TEAM_SYNC(1);
                 if (g0.n) run_phase_a<S>(g0, 0, ta);
                 run_phase_a<H>(g1, i0, ta);
-                TEAM_SYNC(1);
+                WARP_SYNC();
                 if (g0.n) run_phase_b<S>(g0, 0, q, ta);
                 run_phase_b<H>(g1, i0, q, ta);
-                TEAM_SYNC(1);
+                WARP_SYNC();
                 if (g0.n) run_phase_c<S>(sc, g0, 0, q, ta);
                 run_phase_c<H>(sc, g1, i0, q, ta);
-                TEAM_SYNC(1);
+                WARP_SYNC();
                 if (g0.n) run_phase_d<S>(sc, g0, 0, ta);
                 run_phase_d<H>(sc, g1, i0, ta);
                 TEAM_SYNC(1);
@@ -1415,9 +1416,9 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
                 run_borders<4>(g2, 0, tb);
                 TEAM_SYNC(2);
                 run_phase_a<4>(g2, 0, tb);
-                TEAM_SYNC(2);
+                WARP_SYNC();
                 run_phase_b<4>(g2, 0, q, tb);
-                TEAM_SYNC(2);
+                WARP_SYNC();
                 run_phase_c<4>(sc, g2, 0, q, tb);
                 TEAM_SYNC(2);
                 TEAM_PROF(P_TB_PIX, NT / 2);
