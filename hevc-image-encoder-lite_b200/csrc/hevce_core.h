@@ -512,8 +512,8 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 // consecutive items, groups start at multiples of T), so the hand-over needs no CTA- or team-wide barrier
 #define WARP_SYNC() __syncwarp()
 #if defined(HEVCE_PROFILE)   // per-phase latency histogram (development builds only)
-extern __device__ unsigned long long g_phase_cycles[24];
-extern __device__ unsigned long long g_phase_count[24];
+extern __device__ unsigned long long g_phase_cycles[64];
+extern __device__ unsigned long long g_phase_count[64];
 #define PHASE_END_T(tag) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_ = clock64(); \
     atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - sm.prof_last)); atomicAdd(&g_phase_count[tag], 1ull); sm.prof_last = t_; } } while (0)
 #define TEAM_PROF_BEGIN() long long tp_ = clock64()
@@ -1455,12 +1455,24 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
     // nodes one more lane per picture codes the NxN CU as a whole
     {
         constexpr int NC = GANG_RT * NMODE;
-        GANG_FOR(L, 2 * NC + (S == 8 ? GANG_RT : 0)) {
-            if (L < 2 * NC) {
-                const int step = L >= NC, r = L - step * NC, pic = r / NMODE, m = r - pic * NMODE;
-                trial_lane<S>(gang_sm(pic), pic, step * NMODE + m, depth, y0, x0);
-            } else nxn_trial(gang_sm(L - 2 * NC), L - 2 * NC, depth, y0, x0);
+#if defined(HEVCE_PROFILE) && defined(__CUDA_ARCH__)
+        const long long tw0_ = clock64();
+#endif
+        constexpr int NCP = (NC + 31) & ~31;   // every step starts on a warp boundary: one-TU, four-TU and NxN lanes run
+                                               // different code and would serialise inside a shared warp
+        GANG_FOR(L, 2 * NCP + (S == 8 ? GANG_RT : 0)) {
+            if (L < 2 * NCP) {
+                const int step = L >= NCP, r = L - step * NCP, pic = r / NMODE, m = r - pic * NMODE;
+                if (r < NC) trial_lane<S>(gang_sm(pic), pic, step * NMODE + m, depth, y0, x0);
+            } else nxn_trial(gang_sm(L - 2 * NCP), L - 2 * NCP, depth, y0, x0);
         }
+#if defined(HEVCE_PROFILE) && defined(__CUDA_ARCH__)
+        __syncwarp();
+        if (S == 8 && (threadIdx.x & 31) == 0) {   // per-warp duration of the 8x8 trial pass
+            atomicAdd(&g_phase_cycles[24 + threadIdx.x / 32], (unsigned long long)(clock64() - tw0_));
+            atomicAdd(&g_phase_count[24 + threadIdx.x / 32], 1ull);
+        }
+#endif
     }
     PHASE_END_T(P_TRIAL);
 
