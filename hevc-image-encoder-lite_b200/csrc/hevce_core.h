@@ -460,7 +460,10 @@ struct Shared {
     int stream_pos;
     int error;
     long long prof_last;
+    int bank_pad[8];                    // picture stride = 4 (mod 32) words: when a warp of trial lanes straddles two pictures, the
+                                        // lane-private context columns of both still fall into (almost) distinct banks
 };
+static_assert(sizeof(Shared) % 16 == 0 && (sizeof(Shared) / 4) % 32 == 4, "picture stride must be 4 banks (see bank_pad)");
 
 HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CODER); }
 
@@ -512,8 +515,8 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 // consecutive items, groups start at multiples of T), so the hand-over needs no CTA- or team-wide barrier
 #define WARP_SYNC() __syncwarp()
 #if defined(HEVCE_PROFILE)   // per-phase latency histogram (development builds only)
-extern __device__ unsigned long long g_phase_cycles[64];
-extern __device__ unsigned long long g_phase_count[64];
+extern __device__ unsigned long long g_phase_cycles[128];
+extern __device__ unsigned long long g_phase_count[128];
 #define PHASE_END_T(tag) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_ = clock64(); \
     atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - sm.prof_last)); atomicAdd(&g_phase_count[tag], 1ull); sm.prof_last = t_; } } while (0)
 #define TEAM_PROF_BEGIN() long long tp_ = clock64()
@@ -1207,9 +1210,13 @@ HEVCE_HD HEVCE_NOINLINE void run_phase_d_free(const Grp& gref, int first) {
 // candidates (T = S/2), group 2 (S = 8 only) = NxN PU candidates (T = 4)
 template <int S> struct Plan {
     static constexpr int H = S / 2;
-    static constexpr int N0 = S == 8 ? 35 : S == 16 ? 6 : 2;     // one-TU candidates per round
-    static constexpr int N1 = S == 32 ? 7 : 35;                  // four-TU candidates per chunk
-    static constexpr int ROUNDS = S == 32 ? 20 : S == 16 ? 6 : 4; // 32: 5 chunks of 7 modes x 4 sub-TUs; 16: 4 sub-TU rounds + 2 one-TU-only
+    // 32x32 nodes run in two stages that reuse the pool: R0 one-TU rounds of 4 candidates (128 line items of T = 32: one
+    // full pass), then 3 chunks of 12 four-TU candidates x 4 sub-TUs.  Mixing both in one round left the 64 threads
+    // without a 32-point line idle most of the time.
+    static constexpr int N0 = S == 8 ? 35 : S == 16 ? 6 : 4;     // one-TU candidates per round
+    static constexpr int N1 = S == 32 ? 12 : 35;                 // four-TU candidates per chunk
+    static constexpr int R0 = S == 32 ? 9 : 0;                   // 32: one-TU-only rounds that come first
+    static constexpr int ROUNDS = S == 32 ? R0 + 12 : S == 16 ? 6 : 4; // 16: 4 sub-TU rounds + 2 one-TU-only
     static constexpr int al(int v) { return (v + 15) & ~15; }
     // group 0
     static constexpr int BLK0 = 0;
@@ -1218,7 +1225,7 @@ template <int S> struct Plan {
     static constexpr int BORD0 = PSUM0 + al(N0 * S * S);         // S*S/4 ints
     static constexpr int END0 = BORD0 + al(2 * Dim<S>::BS);
     // group 1
-    static constexpr int BLK1 = END0;
+    static constexpr int BLK1 = S == 32 ? 0 : END0;
     static constexpr int PRED1 = BLK1 + al(N1 * Dim<H>::BLK * 2);
     static constexpr int PSUM1 = PRED1 + al(N1 * H * H);
     static constexpr int BORD1 = PSUM1 + al(N1 * H * H);
@@ -1231,7 +1238,7 @@ template <int S> struct Plan {
     static constexpr int BORD2 = PSUM2 + al(35 * 16);
     static constexpr int REC2 = BORD2 + al(2 * Dim<4>::BS);
     static constexpr int END2 = REC2 + al(35 * 16);
-    static constexpr int TOTAL = S == 8 ? END2 : END1;
+    static constexpr int TOTAL = S == 8 ? END2 : S == 32 ? (END0 > END1 ? END0 : END1) : END1;
     static_assert(TOTAL <= POOL_BYTES, "shared-memory pool too small");
     static_assert(S != 8 || TOTAL <= AUX_CODER, "8x8 pipeline buffers overlap the trial-coder results");
 };
@@ -1331,7 +1338,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         Grp g;
         int m0, n;
         if (S == 8) { m0 = 0; n = r == 0 ? 35 : 0; }
-        else { m0 = r * P::N0; n = imax(0, imin(P::N0, NMODE - m0)); }
+        else { m0 = r * P::N0; n = (S == 32 && r >= P::R0) ? 0 : imax(0, imin(P::N0, NMODE - m0)); }
         g.n = n; g.cand0 = m0; g.mode0 = m0; g.ty = y0; g.tx = x0; g.av = av; g.priv = 0;
         g.cuy = y0; g.cux = x0; g.cus = S; g.tu = 0; g.one_tu = 1; g.grec = 1;
         g.blk = P::BLK0; g.pred = P::PRED0; g.psum = P::PSUM0; g.bord = P::BORD0;
@@ -1340,8 +1347,8 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
     };
     auto group1 = [&](int r) -> Grp {   // four-TU candidates: sub-TU k of a chunk of modes, each with its own reconstruction as neighbour
         Grp g;
-        const int k = r & 3, chunk = r >> 2;   // 32x32 nodes only: chunks of four-TU modes
-        const int m0 = chunk * P::N1, n = (S == 16 && r >= 4) ? 0 : imax(0, imin(P::N1, NMODE - m0));
+        const int rr = r - P::R0, k = rr & 3, chunk = rr >> 2;   // 32x32 nodes only: chunks of four-TU modes
+        const int m0 = chunk * P::N1, n = ((S == 16 && r >= 4) || rr < 0) ? 0 : imax(0, imin(P::N1, NMODE - m0));
         g.n = n; g.cand0 = NMODE + m0; g.mode0 = m0; g.ty = y0 + (k >> 1) * H; g.tx = x0 + (k & 1) * H; g.av = sub_avail(av, k); g.priv = 1;
         g.cuy = y0; g.cux = x0; g.cus = S; g.tu = k; g.one_tu = 0; g.grec = 1;
         g.blk = P::BLK1; g.pred = P::PRED1; g.psum = P::PSUM1; g.bord = P::BORD1;
@@ -1468,9 +1475,10 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         }
 #if defined(HEVCE_PROFILE) && defined(__CUDA_ARCH__)
         __syncwarp();
-        if (S == 8 && (threadIdx.x & 31) == 0) {   // per-warp duration of the 8x8 trial pass
-            atomicAdd(&g_phase_cycles[24 + threadIdx.x / 32], (unsigned long long)(clock64() - tw0_));
-            atomicAdd(&g_phase_count[24 + threadIdx.x / 32], 1ull);
+        if ((threadIdx.x & 31) == 0) {   // per-warp duration of the trial pass, by node size
+            constexpr int base = S == 8 ? 24 : S == 16 ? 48 : 72;
+            atomicAdd(&g_phase_cycles[base + threadIdx.x / 32], (unsigned long long)(clock64() - tw0_));
+            atomicAdd(&g_phase_count[base + threadIdx.x / 32], 1ull);
         }
 #endif
     }

@@ -38,8 +38,8 @@ using namespace hevce;
 __device__ Tables g_tables;
 #if defined(HEVCE_PROFILE)
 namespace hevce {
-__device__ unsigned long long g_phase_cycles[64];
-__device__ unsigned long long g_phase_count[64];
+__device__ unsigned long long g_phase_cycles[128];
+__device__ unsigned long long g_phase_count[128];
 }
 #endif
 
@@ -463,7 +463,7 @@ extern "C" void hevce_session_destroy(hevce_session* s) {
 
 #if defined(HEVCE_PROFILE)
 extern "C" __attribute__((visibility("default"))) void hevce_profile_dump(void) {
-    unsigned long long c[64], n[64];
+    unsigned long long c[128], n[128];
     cudaMemcpyFromSymbol(c, g_phase_cycles, sizeof c);
     cudaMemcpyFromSymbol(n, g_phase_count, sizeof n);
     static const char* names[] = {"border", "A", "B", "C", "D+pu/trial", "pu_argmin", "trial(S>8)", "decide", "adopt", "enter", "load", "commit", "misc", "teamA/round", "teamB pixel", "teamB d+cabac", "teamB argmin"};
@@ -471,8 +471,9 @@ extern "C" __attribute__((visibility("default"))) void hevce_profile_dump(void) 
     for (int i = 0; i < P_TA; i++) tot += c[i];   // team tags overlap "D+pu/trial" of the 8x8 nodes
     for (int i = 0; i < P_NTAGS; i++)
         printf("phase %-12s count %10llu cycles %14llu  %5.1f%%  avg %8.0f\n", names[i], n[i], c[i], 100.0 * c[i] / (double)tot, n[i] ? (double)c[i] / n[i] : 0.0);
-    for (int w = 0; w < 24; w++)
-        if (n[24 + w]) printf("8x8 trial pass, warp %2d: avg %8.0f cycles\n", w, (double)c[24 + w] / n[24 + w]);
+    for (int sz = 0; sz < 3; sz++)
+        for (int w = 0; w < 15; w++)
+            if (n[24 + 24 * sz + w]) printf("%dx%d trial pass, warp %2d: avg %8.0f cycles\n", 8 << sz, 8 << sz, w, (double)c[24 + 24 * sz + w] / n[24 + 24 * sz + w]);
 }
 #endif
 
