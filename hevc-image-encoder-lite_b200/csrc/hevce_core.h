@@ -450,7 +450,7 @@ struct Shared {
     s16* ctu_lev;                       // level store of the current CTU (Job::levs + ctu*1024)
     Scratch sc;                         // this picture slot's global scratch (trial lanes may run on another picture's threads)
     int q;                              // qpd6
-    int cand_sse[NCAND], cand_bits[NCAND];
+    int cand_sse[NCAND], cand_bits[NCAND];   // cand_bits: trial bits; RD cost once a one-TU / four-TU lane has finished
     unsigned cgnz[NCAND][4];            // non-zero-group bitmaps: one-TU: [0],[1] = low/high word; else [tu]
     int rate6[6];                       // RDOQ: weighted rate of levels 0..5
     int nxn_pm[4], nxn_cost;
@@ -905,7 +905,7 @@ template <int T> struct Dim {
 struct BSrc { int kind, off; };   // kind 0: constant 128, 1: window byte offset, 2: offset inside the candidate's edge block
 
 template <int T>
-HEVCE_HD inline void border_column(Shared& sm, const Grp& g, int j) {
+HEVCE_HD inline void border_column(Shared& sm, const Grp& g, int j, int c0, int c1) {   // candidates [c0, c1) of a private group
     constexpr int BS = Dim<T>::BS;
     const Avail& a = g.av;
     auto pos = [&](int y, int x) -> BSrc {
@@ -950,7 +950,7 @@ HEVCE_HD inline void border_column(Shared& sm, const Grp& g, int j) {
         const u8* edges = sm.pool + g.rec;
         auto fetch = [&](const BSrc& q, int c) -> int { return q.kind == 1 ? win[q.off] : q.kind == 2 ? edges[c * (4 * T) + q.off] : 128; };
         u8* dst = sm.pool + g.bord + 1 + j;
-        for (int c = 0; c < g.n; c++) {
+        for (int c = c0; c < c1; c++) {
             int v = fetch(s0, c);
             if (inner && use_filtered(T, g.mode0 + c)) v = (2 + 2 * v + fetch(sa, c) + fetch(sb, c)) >> 2;
             dst[c * BS] = (u8)v;
@@ -1164,7 +1164,14 @@ HEVCE_HD HEVCE_NOINLINE void run_borders(const Grp& gref, int off, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
     if (g.n == 0) return;
-    PAR_FOR_TEAM(j, 4 * T + 1, tm.t0, tm.nthr, off) border_column<T>(sm, g, j);
+    if (!g.priv) { PAR_FOR_TEAM(j, 4 * T + 1, tm.t0, tm.nthr, off) border_column<T>(sm, g, j, 0, 0); }
+    else {   // private neighbours: the candidate loop of one border index is shared by four work items
+        const int per = (g.n + 3) >> 2;
+        PAR_FOR_TEAM(it, 4 * (4 * T + 1), tm.t0, tm.nthr, off) {
+            const int j = it >> 2, c0 = (it & 3) * per;
+            border_column<T>(sm, g, j, c0, imin(g.n, c0 + per));
+        }
+    }
 }
 template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_phase_a(const Grp& gref, int off, Team tm) {
@@ -1288,8 +1295,12 @@ HEVCE_HD inline void trial_lane(Shared& sm, int pic, int cand, int depth, int y0
         d.lev[0] = lev; d.mlo[0] = sm.cgnz[cand][0]; d.mhi = pu ? 0u : sm.cgnz[cand][1];
     }
     code_cu<Bac, MainEnv>(b, pic, sm_off(sm, sm.lane_ctx + slot), 4 * NLANE, d);
-    sm.cand_bits[cand] = coder_len(b.c) - base_len;
-    if (!pu) cand_coder(sm)[cand] = b.c;
+    const int bits = coder_len(b.c) - base_len;
+    if (pu) sm.cand_bits[cand] = bits;
+    else {   // the lane leaves its RD cost (the distortion is complete since phase D) and its end state
+        sm.cand_bits[cand] = rd_cost(rd_consts(sm.q), sm.cand_sse[cand], bits);
+        cand_coder(sm)[cand] = b.c;
+    }
 }
 
 // The NxN CU as a whole, trial-coded from the node snapshot (HEVCe.c:1531-1544)
@@ -1369,9 +1380,9 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         for (int r = 0; r < P::ROUNDS; r++) {
             const Grp g0 = group0(r), g1 = group1(r);
             const int i0 = g0.n * S;
-            // ---- phase 0: reference samples
-            run_borders<S>(g0, 0, all);
-            run_borders<H>(g1, 4 * S + 1, all);
+            // ---- phase 0: reference samples (the one-TU border is the same in every round)
+            if (r == 0) run_borders<S>(g0, 0, all);
+            run_borders<H>(g1, r == 0 ? 4 * S + 1 : 0, all);
             PHASE_END_T(P_BORDER);
             // ---- phases A..D: warp-local hand-over (see WARP_SYNC)
             if (g0.n) run_phase_a<S>(g0, 0, all);
@@ -1493,7 +1504,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             best = rd_cost(rk, sse, coder_len(sm.live) - coder_len(sm.snap[depth]));
         }
         for (int c = 0; c < 2 * NMODE; c++) {   // one-TU modes 0..34, then four-TU modes 0..34 (HEVCe.c:1440, 1476)
-            const int cost = rd_cost(rk, sm.cand_sse[c], sm.cand_bits[c]);
+            const int cost = sm.cand_bits[c];   // RD cost, left by the candidate's trial lane
             if (best >= cost) { best = cost; win = c; }
         }
         if (S == 8 && best >= sm.nxn_cost) win = NCAND;   // HEVCe.c:1546
