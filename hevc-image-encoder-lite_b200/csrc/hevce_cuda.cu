@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "../../include/hevce.h"
@@ -197,6 +198,19 @@ struct hevce_session {
     u8* h_stage = nullptr; size_t c_stage = 0;
 };
 
+// host-side staging copies (user buffers <-> pinned memory) spread over a few threads: at 100 Mpixel/s a single
+// thread's memcpy of a 0.8 GB step is a visible part of the end-to-end time
+template <class F>
+static void parallel_pictures(int n, size_t total_bytes, F&& fn) {
+    unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (total_bytes < ((size_t)16 << 20) || n < 2 * (int)nt) nt = 1;
+    if (nt == 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&, t] { for (int i = (int)t; i < n; i += (int)nt) fn(i); });
+    for (auto& x : th) x.join();
+}
+
 static int stage_reserve(hevce_session* s, size_t need) {
     if (need <= s->c_stage) return 0;
     if (s->h_stage) cudaFreeHost(s->h_stage);
@@ -316,11 +330,12 @@ extern "C" int hevce_session_upload(hevce_session* s, const unsigned char* const
     if (s->n == 0) return 0;
     int rc = stage_reserve(s, s->img_total);
     if (rc) return rc;
-    for (int i = 0; i < s->n; i++) {
+    for (int i = 0; i < s->n; i++)
         if (!imgs[i]) return HEVCE_ERR_ARG;
+    parallel_pictures(s->n, s->img_total, [&](int i) {
         const Job& j = s->jobs[i];
         memcpy(s->h_stage + s->img_off[i], imgs[i], (size_t)std::min(j.src_h, j.H) * j.src_w);
-    }
+    });
     CK(cudaMemcpyAsync(s->d_img, s->h_stage, s->img_total, cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     s->h2d = (long long)s->img_total;
@@ -378,15 +393,18 @@ extern "C" int hevce_session_download(hevce_session* s, unsigned char* const* pb
     }
     CK(cudaStreamSynchronize(s->stream));
     off = s->rcon_total;
+    std::vector<size_t> soff((size_t)s->n);
     for (int i = 0; i < s->n; i++) {
         if (!pbuffers[i] || !img_rcons[i]) return HEVCE_ERR_ARG;
-        const Job& j = s->jobs[i];
-        const size_t len = (size_t)s->results[2 * i];
-        memcpy(img_rcons[i], s->h_stage + s->rcon_off[i], (size_t)j.H * j.W);
-        memcpy(pbuffers[i], s->h_stage + off, len);
-        off += (len + 15) & ~(size_t)15;
-        if (stream_len) stream_len[i] = (int)len;
+        soff[i] = off;
+        off += ((size_t)s->results[2 * i] + 15) & ~(size_t)15;
+        if (stream_len) stream_len[i] = s->results[2 * i];
     }
+    parallel_pictures(s->n, off, [&](int i) {
+        const Job& j = s->jobs[i];
+        memcpy(img_rcons[i], s->h_stage + s->rcon_off[i], (size_t)j.H * j.W);
+        memcpy(pbuffers[i], s->h_stage + soff[i], (size_t)s->results[2 * i]);
+    });
     s->d2h = (long long)(s->rcon_total + bytes + 2 * (size_t)s->n * sizeof(int));
     return status;
 }
