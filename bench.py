@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W              # our arm (N>1: launched by torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU implementation
 
-A "step" is one pass of the hot path over one batch: `--images` (default 888 = 148 SMs x 6 pictures per CTA) synthetic
+A "step" is one pass of the hot path over one batch: `--images` (default 1036 = 148 SMs x 7 pictures per CTA) synthetic
 768x512 pictures PER GPU at qpd6=2 -- BASELINE.json configs[2] sharded (weak scaling: per-GPU work fixed; pictures are
 independent, no collective on the data path, NCCL only carries the timing barrier / max-reduce).
   value : whole-job Mpixel/s with the inputs already resident in HBM (session upload outside the timed region)
@@ -126,7 +126,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images", type=int, default=888, help="pictures per GPU per step (888 = 148 SMs x 6 pictures per CTA: one full wave)")
+    ap.add_argument("--images", type=int, default=1036, help="pictures per GPU per step (1036 = 148 SMs x 7 pictures per CTA: one full wave)")
     ap.add_argument("--qpd6", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=-1, help="pictures for the cpu_baseline leg (-1 = one per host core)")
     ap.add_argument("--no-cpu", action="store_true")

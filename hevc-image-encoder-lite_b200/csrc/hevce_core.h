@@ -35,7 +35,8 @@
 
 // tuning switches: tools/ab_variants.py builds A/B variants of the library with -DHEVCE_OPT_xxx=0/1
 // measured on B200 (tools/ab_variants.py, 888 x 64x64, qpd6=2): LPS4=1 +1.5 %, FLUSH=1 +4 % kernel time -> both off;
-// BINSEL neutral; GANG 6 (80 regs) = GANG 5 (96 regs) > GANG 4 by 12 %.
+// BINSEL neutral; GANG 6 (80 regs) = GANG 5 (96 regs) > GANG 4 by 12 %; GANG 7 (72 regs, possible since the context
+// sets shrank to 26 words) 5.7 % more pictures per second per SM than GANG 6.
 #ifndef HEVCE_OPT_LPS4
 #define HEVCE_OPT_LPS4 0
 #endif
@@ -49,7 +50,7 @@
 #define HEVCE_OPT_BINSEL 1
 #endif
 #ifndef HEVCE_OPT_GANG
-#define HEVCE_OPT_GANG 6
+#define HEVCE_OPT_GANG 7
 #endif
 
 namespace hevce {
@@ -67,14 +68,18 @@ constexpr int GANG = HEVCE_OPT_GANG;            // pictures per CTA (lock-step g
 constexpr int NLANE = 70;          // trial-coder lanes with a private context set (the 35 NxN-PU lanes reuse 0..34)
 constexpr int NCAND = 105;         // trial-coder lanes of a CU node: 35 one-TU + 35 four-TU + 35 NxN-PU candidates
 constexpr int NMODE = 35;
-constexpr int NCTX = 142;          // context bytes, same offsets as the reference struct (HEVCe.c:745-759)
-constexpr int CTXW = 36;           // context words per lane (144 bytes)
+constexpr int NCTX = 104;          // context bytes: the contexts of HEVCe.c:745-759 that a luma-only intra stream can touch
+constexpr int CTXW = 26;           // context words per lane
 constexpr int WP = 65;             // pitch of the CTU reconstruction window (row 0 / col 0 = neighbours)
 constexpr int IMAX = 0x7fffffff;
 constexpr int LANE_ELEMS = CTU * CTU;
 
-enum { CX_SPLIT_CU = 0, CX_PART = 3, CX_YPM = 4, CX_UVPM = 5, CX_SPLIT_TU = 6, CX_YCBF = 9, CX_UVCBF = 11,
-       CX_LASTX = 16, CX_LASTY = 41, CX_SIGCG = 66, CX_SIG = 68, CX_ONE = 112, CX_ABS = 136 };
+// Compact layout (the reference struct also carries the chroma contexts, 142 bytes): split_cu 0-2, part 3, luma mode 4,
+// chroma mode 5, split_tu 6-8, cbf_luma 9-10, cbf_chroma 11, coded_sub_block 12-13, last_x 16-35 (4 sizes x 5), last_y
+// 36-55, sig_coeff 56-82 (27 luma), greater1 84-99 (4 sets x 4), greater2 100-103.  A 4x4 luma TU touches words
+// 4, 9, 14-16, 21-25 only.
+enum { CX_SPLIT_CU = 0, CX_PART = 3, CX_YPM = 4, CX_UVPM = 5, CX_SPLIT_TU = 6, CX_YCBF = 9, CX_UVCBF = 11, CX_SIGCG = 12,
+       CX_LASTX = 16, CX_LASTY = 36, CX_SIG = 56, CX_ONE = 84, CX_ABS = 100 };
 
 HEVCE_HD inline int imin(int a, int b) { return a < b ? a : b; }
 HEVCE_HD inline int imax(int a, int b) { return a > b ? a : b; }
@@ -97,7 +102,7 @@ HEVCE_HD inline int bitlen(unsigned v) {
 struct Tables {
     u32 lps4[64];          // rangeTabLps, one word per state: byte q = LPS range for (range>>6)&3 == q  (HEVCe.c:704-713)
     u8 next_lps[128];      // (state<<1|mps) after an LPS                   (HEVCe.c:702)
-    u8 ctx_iv[144];        // context init values by byte offset            (HEVCe.c:763-777)
+    u8 ctx_iv[4 * CTXW];   // context init values by (compact) context index    (HEVCe.c:763-777)
     u8 scan4[3][16];       // in-CG scan, (y<<2)|x : diag / horizontal / vertical
     u8 inv4[3][16];        // inverse: raster index (y<<2)|x -> scan index
     u32 sigoff[3][4];      // sig_coeff ctx offset (2 bits per scan index) by neighbour pattern (HEVCe.c:1116-1121)
@@ -137,14 +142,15 @@ inline void fill_tables(Tables& t) {
     for (int s = 0; s < 64; s++) t.lps4[s] = (u32)LPS[s][0] | ((u32)LPS[s][1] << 8) | ((u32)LPS[s][2] << 16) | ((u32)LPS[s][3] << 24);
     for (int s = 0; s < 64; s++)
         for (int m = 0; m < 2; m++) t.next_lps[(s << 1) | m] = (u8)((TRANS_LPS[s] << 1) | (s == 0 ? !m : m));
-    for (int i = 0; i < 144; i++) t.ctx_iv[i] = 154;
-    for (int i = 0; i < 16; i++) t.ctx_iv[i] = HEAD[i];
-    for (int i = 0; i < 25; i++) t.ctx_iv[CX_LASTX + i] = t.ctx_iv[CX_LASTY + i] = LAST[i];
+    // the init tables are in the reference's order (luma entries first in every group); only the luma part is kept
+    for (int i = 0; i < 4 * CTXW; i++) t.ctx_iv[i] = 154;
+    for (int i = 0; i < 12; i++) t.ctx_iv[i] = HEAD[i];
+    for (int i = 0; i < 20; i++) t.ctx_iv[CX_LASTX + i] = t.ctx_iv[CX_LASTY + i] = LAST[i];
     t.ctx_iv[CX_SIGCG] = 91;
     t.ctx_iv[CX_SIGCG + 1] = 171;
-    for (int i = 0; i < 44; i++) t.ctx_iv[CX_SIG + i] = SIG[i];
-    for (int i = 0; i < 24; i++) t.ctx_iv[CX_ONE + i] = ONE[i];
-    for (int i = 0; i < 6; i++) t.ctx_iv[CX_ABS + i] = ABSV[i];
+    for (int i = 0; i < 27; i++) t.ctx_iv[CX_SIG + i] = SIG[i];
+    for (int i = 0; i < 16; i++) t.ctx_iv[CX_ONE + i] = ONE[i];
+    for (int i = 0; i < 4; i++) t.ctx_iv[CX_ABS + i] = ABSV[i];
     // scans: up-right diagonal / raster / column-major, same pattern inside a CG and over the CG grid (HEVCe.c:1128-1132)
     for (int type = 0; type < 3; type++) {
         int n = 0;
@@ -385,7 +391,7 @@ struct CtuRec {          // what the commit pass needs for one CTU (written by t
     Coder start, end;    // coder state before the CTU / after its terminate bin (and the final flush for the last CTU)
     int out_pos;         // byte offset of this CTU's bytes in the stream
     int last;            // 1: last CTU of the picture
-    u8 ctx[144];         // contexts at CTU start
+    u8 ctx[4 * CTXW];    // contexts at CTU start
     u8 msz[84], mpm[84]; // neighbour maps after the CTU was decided ([1+uy][1+ux], 81 used)
     u8 kind[16];
 };
@@ -437,10 +443,10 @@ constexpr int AUX_CODER = 16640;        // pool tail: trial-coder results (free 
 struct Shared {
     alignas(16) u8 pool[POOL_BYTES];    // per-node carve-up: work blocks, predictions, borders (see Plan<S>)
     u32 lane_ctx[CTXW * NLANE];         // lane-private context sets, word-interleaved
-    alignas(16) u8 ctx0[144];           // freshly initialised contexts for this picture's qpd6
-    alignas(16) u8 live_ctx[144];
-    alignas(16) u8 snap_ctx[3][144];
-    alignas(16) u8 nxn_ctx[144];
+    alignas(16) u8 ctx0[4 * CTXW];      // freshly initialised contexts for this picture's qpd6
+    alignas(16) u8 live_ctx[4 * CTXW];
+    alignas(16) u8 snap_ctx[3][4 * CTXW];
+    alignas(16) u8 nxn_ctx[4 * CTXW];
     alignas(16) s16 nxn_lev[4][16];
     u8 orig[CTU * CTU];
     u8 win[(CTU + 1) * WP];
@@ -460,10 +466,7 @@ struct Shared {
     int stream_pos;
     int error;
     long long prof_last;
-    int bank_pad[8];                    // picture stride = 4 (mod 32) words: when a warp of trial lanes straddles two pictures, the
-                                        // lane-private context columns of both still fall into (almost) distinct banks
 };
-static_assert(sizeof(Shared) % 16 == 0 && (sizeof(Shared) / 4) % 32 == 4, "picture stride must be 4 banks (see bank_pad)");
 
 HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CODER); }
 
@@ -1272,12 +1275,12 @@ HEVCE_HD inline void trial_lane(Shared& sm, int pic, int cand, int depth, int y0
     Bac b = make_bac(sm.snap[depth]);
     if (pu) coder_reset(b.c);
     const int base_len = pu ? coder_len(b.c) : coder_len(sm.snap[depth]);
-    if (pu) {   // a 4x4 luma TU touches last_x/y row 0 (words 4,5,10,11), sig 0..8 (17-19), greater1 0..15 (28-31), greater2 0..3 (34)
+    if (pu) {   // a 4x4 luma TU touches last_x/y row 0 (words 4, 9), sig 0..8 (14-16), greater1 0..15 (21-24), greater2 0..3 (25)
         const u32* src = (const u32*)sm.ctx0;
         u32* dst = sm.lane_ctx + slot;
-        const int W4[12] = {4, 5, 10, 11, 17, 18, 19, 28, 29, 30, 31, 34};
+        const int W4[10] = {4, 9, 14, 15, 16, 21, 22, 23, 24, 25};
 #pragma unroll
-        for (int k = 0; k < 12; k++) dst[W4[k] * NLANE] = src[W4[k]];
+        for (int k = 0; k < 10; k++) dst[W4[k] * NLANE] = src[W4[k]];
     } else {
         const u32* src = (const u32*)sm.snap_ctx[depth];
         u32* dst = sm.lane_ctx + slot;
@@ -1624,7 +1627,7 @@ HEVCE_HD inline void commit_ctu(const Job& job, int ctu, int lane) {
     if (!coder_equal(b.c, r.end)) err |= ERR_COMMIT_MISMATCH;   // the adopted trial state must be what the bytes produce
     if (!r.last) {
         const u32* nx = (const u32*)job.recs[ctu + 1].ctx;
-        for (int k = 0; k < CTXW - 1; k++) if (cw[k * NT] != nx[k]) err |= ERR_COMMIT_MISMATCH;
+        for (int k = 0; k < CTXW; k++) if (cw[k * NT] != nx[k]) err |= ERR_COMMIT_MISMATCH;
     }
     if (b.c.n > b.cap) err |= ERR_OVERFLOW;
     if (err) HEVCE_ATOMIC_OR(job.result + 1, err);
@@ -1672,8 +1675,8 @@ HEVCE_HD inline int write_header(u8* out, int q, int H, int W) {
 // ------------------------------------------------------------------------------------------------------------
 HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared& sm, const Scratch& sc) {
     const int q = job.q, H = job.H, W = job.W;
-    PAR_FOR(i, 144) {
-        const u8 v = i < NCTX ? ctx_init_value(my_tb().ctx_iv[i], q) : (u8)0;
+    PAR_FOR(i, 4 * CTXW) {
+        const u8 v = ctx_init_value(my_tb().ctx_iv[i], q);
         sm.ctx0[i] = v;
         sm.live_ctx[i] = v;
     }
