@@ -1490,7 +1490,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
 #if defined(HEVCE_PROFILE) && defined(__CUDA_ARCH__)
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {   // per-warp duration of the trial pass, by node size
-            constexpr int base = S == 8 ? 24 : S == 16 ? 48 : 72;
+            constexpr int base = S == 8 ? 24 : S == 16 ? 56 : 88;   // 32 warp slots per node size
             atomicAdd(&g_phase_cycles[base + threadIdx.x / 32], (unsigned long long)(clock64() - tw0_));
             atomicAdd(&g_phase_count[base + threadIdx.x / 32], 1ull);
         }

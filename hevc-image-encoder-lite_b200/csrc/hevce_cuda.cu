@@ -490,8 +490,8 @@ extern "C" __attribute__((visibility("default"))) void hevce_profile_dump(void) 
     for (int i = 0; i < P_NTAGS; i++)
         printf("phase %-12s count %10llu cycles %14llu  %5.1f%%  avg %8.0f\n", names[i], n[i], c[i], 100.0 * c[i] / (double)tot, n[i] ? (double)c[i] / n[i] : 0.0);
     for (int sz = 0; sz < 3; sz++)
-        for (int w = 0; w < 15; w++)
-            if (n[24 + 24 * sz + w]) printf("%dx%d trial pass, warp %2d: avg %8.0f cycles\n", 8 << sz, 8 << sz, w, (double)c[24 + 24 * sz + w] / n[24 + 24 * sz + w]);
+        for (int w = 0; w < 32; w++)
+            if (n[24 + 32 * sz + w] && c[24 + 32 * sz + w] / n[24 + 32 * sz + w] > 1000) printf("%dx%d trial pass, warp %2d: avg %8.0f cycles\n", 8 << sz, 8 << sz, w, (double)c[24 + 32 * sz + w] / n[24 + 32 * sz + w]);
 }
 #endif
 

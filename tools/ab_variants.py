@@ -25,7 +25,7 @@ if sys.argv[1] == "build":
         out, _ = p.communicate()
         print(spec, "ok" if p.returncode == 0 else "FAILED\n" + out[-2000:])
 else:
-    args = sys.argv[2:] or ["888", "64", "64", "2"]
+    args = sys.argv[2:] or ["1036", "64", "64", "2"]
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import workloads as WL
