@@ -192,6 +192,7 @@ struct hevce_session {
     CtuRec* d_recs = nullptr; size_t c_recs = 0;
     unsigned long long* d_sse = nullptr; size_t c_sse = 0;
     float quality_ms = 0.f;
+    bool encoded = false;   // hevce_session_encode has run since the last configure/upload
     std::vector<size_t> ctu_off;
     int line_pitch = 0;
     // pinned staging
@@ -226,6 +227,7 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     int rc = device_prepare(s->device);
     if (rc) return rc;
     const int max_dim = hevce_internal_max_dim();
+    s->encoded = false;
     s->n = n;
     s->jobs.assign(n, Job());
     s->img_off.assign(n, 0); s->rcon_off.assign(n, 0); s->out_off.assign(n, 0); s->ctu_off.assign(n, 0);
@@ -339,6 +341,7 @@ extern "C" int hevce_session_upload(hevce_session* s, const unsigned char* const
     CK(cudaMemcpyAsync(s->d_img, s->h_stage, s->img_total, cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     s->h2d = (long long)s->img_total;
+    s->encoded = false;
     return 0;
 }
 
@@ -362,6 +365,7 @@ extern "C" int hevce_session_encode(hevce_session* s) {
     CK(cudaEventElapsedTime(&s->kernel_ms, s->ev0, s->ev1));
     CK(cudaEventElapsedTime(&s->commit_ms, s->ev1, s->ev2));
     s->launches += 2;
+    s->encoded = true;
     return 0;
 }
 
@@ -412,6 +416,7 @@ extern "C" int hevce_session_download(hevce_session* s, unsigned char* const* pb
 // f3: per-picture MSE / PSNR of the last encode, reduced on the device (calcImagePSNR, HEVCeMain.c:116-133)
 extern "C" int hevce_session_quality(hevce_session* s, double* mse, double* psnr) {
     if (!s || (s->n > 0 && !mse && !psnr)) return HEVCE_ERR_ARG;
+    if (s->n > 0 && !s->encoded) return HEVCE_ERR_STATE;   // nothing has been encoded yet
     CK(cudaSetDevice(s->device));
     if (s->n == 0) return 0;
     int rc = grow(&s->d_sse, &s->c_sse, (size_t)s->n);
@@ -444,6 +449,7 @@ extern "C" float hevce_session_quality_ms(const hevce_session* s) { return s ? s
 // CU kind per 8x8 unit ((H/8)*(W/8) bytes: 0 one TU, 1 four TUs, 2 NxN).  Any pointer may be NULL.
 extern "C" int hevce_session_partition(hevce_session* s, int i, unsigned char* cu_size, unsigned char* mode, unsigned char* kind) {
     if (!s || i < 0 || i >= s->n) return HEVCE_ERR_ARG;
+    if (!s->encoded) return HEVCE_ERR_STATE;               // nothing has been encoded yet
     CK(cudaSetDevice(s->device));
     const Job& j = s->jobs[i];
     std::vector<CtuRec> recs((size_t)(j.H / CTU) * (j.W / CTU));

@@ -76,7 +76,8 @@ HEVCE_API int  hevce_session_launches(const hevce_session *s);     /* kernel lau
 HEVCE_API int  hevce_session_grid(const hevce_session *s);         /* CTAs of the persistent encode grid */
 /* Per-picture quality of the last encode, reduced on the device: mean squared error and PSNR between source and
  * reconstruction over the area both cover, MSE floored at 1e-9 (calcImagePSNR, HEVCeMain.c:116-133, printed by the
- * reference CLI at HEVCeMain.c:201-212).  mse / psnr: n doubles each, either may be NULL. */
+ * reference CLI at HEVCeMain.c:201-212).  mse / psnr: n doubles each, either may be NULL.  HEVCE_ERR_STATE before the
+ * first hevce_session_encode of the uploaded pictures (the same holds for hevce_session_partition). */
 HEVCE_API int  hevce_session_quality(hevce_session *s, double *mse, double *psnr);
 HEVCE_API float hevce_session_quality_ms(const hevce_session *s);  /* CUDA-event duration of the last hevce_quality_kernel launch */
 /* Decisions of picture i of the last encode as raster maps: CU size (8/16/32) and luma intra mode (0..34) per 4x4 unit,

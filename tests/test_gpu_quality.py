@@ -130,3 +130,18 @@ def test_quality_study_on_the_batch_api(H, tmp_path):
         assert r["HEVC"][1] == pytest.approx(8.0 * len(s) / rc.size)
         assert abs(r["JPEG"][0] - r["HEVC"][0]) < 0.02 and os.path.exists(base + ".jpg") and os.path.exists(base + ".webp")
     assert means["JPEG"] > means["HEVC"]
+
+
+def test_quality_and_partition_need_an_encode(H):
+    img = np.full((40, 40), 9, np.uint8)
+    ses = H.Session(0, [img.shape], 1)
+    ses.upload([img])
+    with pytest.raises(H.HevceError) as e1:
+        ses.quality()
+    with pytest.raises(H.HevceError) as e2:
+        ses.partition(0)
+    assert e1.value.code == H.ERR_STATE and e2.value.code == H.ERR_STATE
+    ses.encode()
+    mse, _ = ses.quality()
+    assert mse[0] >= 1e-9
+    ses.close()
