@@ -482,6 +482,15 @@ __device__ __forceinline__ Shared& gang_sm(int p) { return reinterpret_cast<Shar
 inline Shared& my_sm() { return *static_cast<Shared*>(nullptr); }   // host pass of nvcc: declared, never executed
 inline Shared& gang_sm(int) { return *static_cast<Shared*>(nullptr); }
 inline Tables& my_tb() { return *static_cast<Tables*>(nullptr); }
+#elif defined(HEVCE_SIM_GANG)
+// gang simulator (tests/sim): one host thread per picture of a gang, real barriers between the phases
+extern Shared* g_sim_sms;                                            // GANG picture blocks
+extern Tables* g_sim_tb;
+extern thread_local int g_sim_member;                                // this thread's picture slot
+void sim_barrier(int id);                                            // 0: CTA-wide, 1 / 2: the two teams
+inline Shared& my_sm() { return g_sim_sms[g_sim_member]; }
+inline Shared& gang_sm(int p) { return g_sim_sms[p]; }
+inline Tables& my_tb() { return *g_sim_tb; }
 #else
 extern Shared* g_sim_sm;                                             // CTA simulator (tests/sim)
 extern Tables* g_sim_tb;
@@ -505,6 +514,7 @@ static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail to
 // spans the same team of all pictures of the gang (their trial lanes are packed across pictures)
 #define TEAM_A if (HEVCE_TID < NT / 2)
 #define TEAM_B else
+#define TEAM_JOIN() ((void)0)   // the CTA-wide barrier that follows is the join
 #define TEAM_SYNC(id) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(GANG * NT / 2) : "memory")
 // Trial-coder lanes are packed across the pictures of the gang (full warps): lane L of the CTA, or lane u of the
 // "upper half" threads (threads 64..127 of every picture) while the lower halves run phase-D items.
@@ -545,20 +555,45 @@ inline int sim_item(int i, int n) {
 #define PAR_FOR(item, n) for (int item##_i = 0, item = 0; item##_i < (n) && ((item = sim_item(item##_i, (n))), true); item##_i++)
 #define PAR_FOR_OFF(item, n, off) PAR_FOR(item, n)
 #define PAR_FOR_TEAM(item, n, t0, nthr, off) PAR_FOR(item, n)
+#if defined(HEVCE_SIM_GANG)
+// the two teams of a picture really run side by side: team A on a helper thread, team B on the picture's thread
+#define TEAM_A auto team_a_ = [&](int member_) { g_sim_member = member_;
+#define TEAM_B }; std::thread team_a_thread_(team_a_, g_sim_member);
+#define TEAM_JOIN() team_a_thread_.join()
+#else
 #define TEAM_A
 #define TEAM_B
+#define TEAM_JOIN() ((void)0)
+#endif
+#define WARP_SYNC() ((void)0)
+#define TEAM_PROF_BEGIN() ((void)0)
+#define TEAM_PROF(tag, lead) ((void)0)
+#if defined(HEVCE_SIM_GANG)
+// Host thread m stands for the NT threads of picture slot m: it runs the gang-wide loops for exactly the lane / thread
+// indices those threads own on the GPU, so the cross-picture packing and the barrier structure are exercised for real
+// (each thread runs its team A section, then its team B section; the team barriers span the threads).
+#define GANG_RT GANG
+#define GANG_FOR(L, n) for (int L = g_sim_member * NT; L < (n) && L < (g_sim_member + 1) * NT; L++)
+#define GANG_FOR_UPPER(u, n) for (int u = g_sim_member * (NT / 2); u < (n) && u < (g_sim_member + 1) * (NT / 2); u++)
+#define GANG_FOR_UPPER_FREE(it, first, n) \
+    for (int u_ = g_sim_member * (NT / 2) > (first) ? g_sim_member * (NT / 2) : (first); u_ < (g_sim_member + 1) * (NT / 2); u_++) \
+        for (int it = u_ - (first); it < (n); it += GANG * NT / 2 - (first))
+#define TEAM_SYNC(id) sim_barrier(id)
+#define PHASE_END() sim_barrier(0)
+#define PHASE_END_T(tag) sim_barrier(0)
+#define HEVCE_ATOMIC_OR(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
+#define HEVCE_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
+#else
 #define TEAM_SYNC(id) ((void)0)
 #define GANG_RT 1
 #define GANG_FOR(L, n) PAR_FOR(L, n)
 #define GANG_FOR_UPPER(u, n) PAR_FOR(u, n)
 #define GANG_FOR_UPPER_FREE(it, first, n) PAR_FOR(it, n)
 #define PHASE_END() ((void)0)
-#define WARP_SYNC() ((void)0)
 #define PHASE_END_T(tag) ((void)0)
-#define TEAM_PROF_BEGIN() ((void)0)
-#define TEAM_PROF(tag, lead) ((void)0)
 #define HEVCE_ATOMIC_OR(p, v) (*(p) |= (v))
 #define HEVCE_ATOMIC_ADD(p, v) (*(p) += (v))
+#endif
 #endif
 
 struct Avail { int L, LB, A, AR; };
@@ -1469,6 +1504,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
                 TEAM_PROF(P_TB_ARGMIN, NT / 2);
             }
         }
+        TEAM_JOIN();
         PHASE_END_T(P_D_TRIAL);
     }
 
