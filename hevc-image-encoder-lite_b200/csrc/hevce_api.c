@@ -3,11 +3,16 @@
  *
  *   HEVCImageEncoder       drop-in for the reference entry point (HEVCe.h:5-12, HEVCe.c:1570-1647)
  *   HEVCImageEncoderBatch  n independent pictures, sharded over the selected GPUs by cumulative CTU count,
- *                          one host thread per device, no collective
+ *                          no collective
  *
- * There is no CPU encoder in this library: every picture is encoded by the sm_100a kernel; if no CUDA device can be
+ * A shard (the pictures of one device) is cut into chunks of whole kernel waves; two host threads per device take
+ * alternate chunks, each with its own session (stream + pinned staging), so the host<->device copies of one chunk
+ * overlap the kernel of the other and the second kernel's CTAs fill the SMs the first one's tail leaves idle.
+ *
+ * There is no CPU encoder in this library: every picture is encoded by the sm_100a kernels; if no CUDA device can be
  * used the calls fail with HEVCE_ERR_CUDA.
  */
+#include <errno.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -17,51 +22,57 @@
 
 #define API __attribute__((visibility("default")))
 #define MAX_DEV 64
-#define CHUNK_PIXELS (768LL * 1024 * 1024)   /* per-device sub-batch bound (padded pixels) so staging stays modest */
+#define POOL_PER_DEV 4                        /* cached sessions (grow-only buffers) per device ordinal */
+#define CHUNK_PIXELS (768LL * 1024 * 1024)    /* per-chunk bound (padded pixels) so the pinned staging stays modest */
 #define CHUNK_PICTURES 32768                  /* ... and pictures (the commit kernel's grid.y is the picture index) */
+#define WAVE_PICTURES (148 * 7)               /* pictures of one full wave of the 7-picture variant on a B200 */
 
-static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;   /* device list + session pool */
 static int g_ndev = -1, g_devs[MAX_DEV];
 static int g_max_dim = 8192;
-static hevce_session *g_pool[MAX_DEV];          /* one cached session (grow-only buffers) per device ordinal */
-static pthread_mutex_t g_pool_lock[MAX_DEV];
-static int g_pool_init = 0;
+static hevce_session *g_pool[MAX_DEV][POOL_PER_DEV];
+static int g_pool_busy[MAX_DEV][POOL_PER_DEV];
 
-API const char *hevce_version(void) { return "hevce-b200 0.1 (sm_100a)"; }
+API const char *hevce_version(void) { return "hevce-b200 0.2 (sm_100a)"; }
 
-int hevce_internal_max_dim(void) { return g_max_dim; }
+API int hevce_get_max_dim(void) { return __atomic_load_n(&g_max_dim, __ATOMIC_RELAXED); }
+int hevce_internal_max_dim(void) { return hevce_get_max_dim(); }
 
 API int hevce_set_max_dim(int max_dim) {
-    int old = g_max_dim;
-    if (max_dim >= 32 && max_dim <= 16384) g_max_dim = max_dim;
+    int old = hevce_get_max_dim();
+    if (max_dim >= 32 && max_dim <= 16384) __atomic_store_n(&g_max_dim, max_dim, __ATOMIC_RELAXED);
     return old;
 }
 
-static void init_pool_locks(void) {
-    int i;
-    if (g_pool_init) return;
-    for (i = 0; i < MAX_DEV; i++) pthread_mutex_init(&g_pool_lock[i], NULL);
-    g_pool_init = 1;
-}
-
-static int resolve_devices(void) {   /* call with g_lock held */
+/* HEVCE_DEVICES="0,3": every entry must be a visible ordinal; anything else is an error (nothing is cached) */
+static int resolve_devices(void) {   /* call with g_lock held; returns the device count or a negative HEVCE_ERR_* */
     int visible, i;
-    init_pool_locks();
     if (g_ndev >= 0) return g_ndev;
     visible = hevce_internal_device_count();
-    g_ndev = 0;
     {
         const char *env = getenv("HEVCE_DEVICES");
         if (env && *env) {
-            char *copy = strdup(env), *save = NULL, *tok;
-            for (tok = strtok_r(copy, ",", &save); tok && g_ndev < MAX_DEV; tok = strtok_r(NULL, ",", &save)) {
-                int d = atoi(tok);
-                if (d >= 0 && d < visible) g_devs[g_ndev++] = d;
+            int devs[MAX_DEV], nd = 0;
+            const char *p = env;
+            while (*p) {
+                char *end;
+                long d;
+                errno = 0;
+                d = strtol(p, &end, 10);
+                if (end == p || errno || d < 0 || d >= visible || nd >= MAX_DEV || (*end && *end != ',')) {
+                    fprintf(stderr, "libhevce_b200: HEVCE_DEVICES=\"%s\" is not a list of visible device ordinals (%d visible)\n", env, visible);
+                    return visible ? HEVCE_ERR_ARG : HEVCE_ERR_CUDA;
+                }
+                devs[nd++] = (int)d;
+                p = *end ? end + 1 : end;
             }
-            free(copy);
+            if (nd == 0) return HEVCE_ERR_ARG;
+            memcpy(g_devs, devs, sizeof(int) * (size_t)nd);
+            g_ndev = nd;
             return g_ndev;
         }
     }
+    g_ndev = 0;
     for (i = 0; i < visible && i < MAX_DEV; i++) g_devs[g_ndev++] = i;
     return g_ndev;
 }
@@ -72,52 +83,147 @@ API int hevce_set_devices(int count, const int *ordinals) {
     for (i = 0; i < count; i++)
         if (ordinals[i] < 0 || ordinals[i] >= visible) return visible ? HEVCE_ERR_ARG : HEVCE_ERR_CUDA;
     pthread_mutex_lock(&g_lock);
-    init_pool_locks();
     g_ndev = count;
     for (i = 0; i < count; i++) g_devs[i] = ordinals[i];
     pthread_mutex_unlock(&g_lock);
     return 0;
 }
 
+/* ---- session pool: concurrent callers (and the two chunk workers of a shard) get a session each ---------------- */
+static hevce_session *pool_acquire(int device, int *slot) {
+    int k;
+    hevce_session *s = NULL;
+    *slot = -1;
+    pthread_mutex_lock(&g_lock);
+    for (k = 0; k < POOL_PER_DEV && *slot < 0; k++)
+        if (!g_pool_busy[device][k] && g_pool[device][k]) *slot = k;
+    for (k = 0; k < POOL_PER_DEV && *slot < 0; k++)
+        if (!g_pool_busy[device][k]) *slot = k;
+    if (*slot >= 0) { g_pool_busy[device][*slot] = 1; s = g_pool[device][*slot]; }
+    pthread_mutex_unlock(&g_lock);
+    if (!s) {   /* an empty pool slot, or every pooled session is busy (then the session is temporary) */
+        s = hevce_session_create_empty(device);
+        if (s && *slot >= 0) {
+            pthread_mutex_lock(&g_lock);
+            g_pool[device][*slot] = s;
+            pthread_mutex_unlock(&g_lock);
+        }
+    }
+    return s;
+}
+
+static void pool_release(int device, int slot, hevce_session *s) {
+    if (slot < 0) { hevce_session_destroy(s); return; }
+    pthread_mutex_lock(&g_lock);
+    g_pool_busy[device][slot] = 0;
+    pthread_mutex_unlock(&g_lock);
+}
+
+/* Free the cached sessions (HBM buffers, pinned staging) of every device.  Sessions in use by a running call stay. */
+API void hevce_release(void) {
+    int d, k;
+    for (d = 0; d < MAX_DEV; d++)
+        for (k = 0; k < POOL_PER_DEV; k++) {
+            hevce_session *s = NULL;
+            pthread_mutex_lock(&g_lock);
+            if (!g_pool_busy[d][k]) { s = g_pool[d][k]; g_pool[d][k] = NULL; }
+            pthread_mutex_unlock(&g_lock);
+            if (s) hevce_session_destroy(s);
+        }
+}
+
 typedef struct {
-    int device, first, count, status;
+    int device, first, count, status, max_dim;
     unsigned char *const *pbuffers;
     const unsigned char *const *imgs;
     unsigned char *const *rcons;
     const int *ysz, *xsz, *qpd6;
     int *stream_len;
+    /* chunk queue shared by the shard's workers */
+    int nchunk, next_chunk;
+    int *chunk_first;   /* nchunk + 1 entries */
+    pthread_mutex_t qlock;
 } Shard;
 
-static long long padded_pixels(int h, int w) {
-    long long H = ((h < g_max_dim ? h : g_max_dim) + 31) / 32 * 32, W = ((w < g_max_dim ? w : g_max_dim) + 31) / 32 * 32;
+static long long padded_pixels(int h, int w, int max_dim) {
+    long long H = ((h < max_dim ? h : max_dim) + 31) / 32 * 32, W = ((w < max_dim ? w : max_dim) + 31) / 32 * 32;
     return H * W;
 }
 
-/* encode pictures [first, first+count) on one device, in sub-batches of bounded size */
+/* worker: encode chunks of the shard until the queue is empty */
+static void *chunk_worker(void *arg) {
+    Shard *sh = (Shard *)arg;
+    int slot, saved = hevce_internal_get_device();
+    hevce_session *s = pool_acquire(sh->device, &slot);
+    if (!s) {
+        pthread_mutex_lock(&sh->qlock);
+        if (!sh->status) sh->status = HEVCE_ERR_CUDA;
+        pthread_mutex_unlock(&sh->qlock);
+        return NULL;
+    }
+    for (;;) {
+        int c, a, m, rc;
+        pthread_mutex_lock(&sh->qlock);
+        c = sh->status ? sh->nchunk : sh->next_chunk++;
+        pthread_mutex_unlock(&sh->qlock);
+        if (c >= sh->nchunk) break;
+        a = sh->chunk_first[c];
+        m = sh->chunk_first[c + 1] - a;
+        rc = hevce_session_configure(s, m, sh->ysz + a, sh->xsz + a, sh->qpd6 + a, sh->max_dim);
+        if (!rc) rc = hevce_session_upload(s, sh->imgs + a);
+        if (!rc) rc = hevce_session_encode(s);
+        if (!rc) rc = hevce_session_download(s, sh->pbuffers + a, sh->rcons + a, sh->stream_len + a);
+        if (rc) {
+            pthread_mutex_lock(&sh->qlock);
+            if (!sh->status) sh->status = rc;
+            pthread_mutex_unlock(&sh->qlock);
+        }
+    }
+    pool_release(sh->device, slot, s);
+    hevce_internal_set_device(saved);   /* leave the caller's current device as it was */
+    return NULL;
+}
+
+/* encode pictures [first, first+count) on one device */
 static void *shard_main(void *arg) {
     Shard *sh = (Shard *)arg;
-    int done = 0;
+    int done = 0, cap = 16, wave_ok;
+    pthread_t helper;
     sh->status = 0;
-    pthread_mutex_lock(&g_pool_lock[sh->device]);
-    while (done < sh->count && sh->status == 0) {
-        int a = sh->first + done, m = 0, rc;
+    sh->nchunk = 0;
+    sh->next_chunk = 0;
+    sh->chunk_first = (int *)malloc(sizeof(int) * (size_t)(cap + 1));
+    if (!sh->chunk_first) { sh->status = HEVCE_ERR_ARG; return NULL; }
+    pthread_mutex_init(&sh->qlock, NULL);
+    while (done < sh->count) {
+        int a = sh->first + done, m = 0, same = 1;
         long long px = 0;
-        while (done + m < sh->count && m < CHUNK_PICTURES && (m == 0 || px + padded_pixels(sh->ysz[a + m], sh->xsz[a + m]) <= CHUNK_PIXELS)) {
-            px += padded_pixels(sh->ysz[a + m], sh->xsz[a + m]);
+        while (done + m < sh->count && m < CHUNK_PICTURES &&
+               (m == 0 || px + padded_pixels(sh->ysz[a + m], sh->xsz[a + m], sh->max_dim) <= CHUNK_PIXELS)) {
+            px += padded_pixels(sh->ysz[a + m], sh->xsz[a + m], sh->max_dim);
+            if (sh->ysz[a + m] != sh->ysz[a] || sh->xsz[a + m] != sh->xsz[a]) same = 0;
             m++;
         }
-        if (!g_pool[sh->device]) {
-            g_pool[sh->device] = hevce_session_create(sh->device, m, sh->ysz + a, sh->xsz + a, sh->qpd6 + a);
-            rc = g_pool[sh->device] ? 0 : HEVCE_ERR_CUDA;
-        } else
-            rc = hevce_session_configure(g_pool[sh->device], m, sh->ysz + a, sh->xsz + a, sh->qpd6 + a);
-        if (!rc) rc = hevce_session_upload(g_pool[sh->device], sh->imgs + a);
-        if (!rc) rc = hevce_session_encode(g_pool[sh->device]);
-        if (!rc) rc = hevce_session_download(g_pool[sh->device], sh->pbuffers + a, sh->rcons + a, sh->stream_len + a);
-        sh->status = rc;
+        /* same-size pictures: whole waves of the 7-picture variant per chunk, so no chunk ends with a nearly empty wave */
+        wave_ok = same && m > WAVE_PICTURES && done + m < sh->count;
+        if (wave_ok) m -= m % WAVE_PICTURES;
+        if (sh->nchunk == cap) {
+            int *p = (int *)realloc(sh->chunk_first, sizeof(int) * (size_t)(2 * cap + 1));
+            if (!p) { sh->status = HEVCE_ERR_ARG; break; }
+            sh->chunk_first = p;
+            cap *= 2;
+        }
+        sh->chunk_first[sh->nchunk++] = a;
         done += m;
     }
-    pthread_mutex_unlock(&g_pool_lock[sh->device]);
+    sh->chunk_first[sh->nchunk] = sh->first + sh->count;
+    if (!sh->status) {
+        int have_helper = sh->nchunk > 1 && pthread_create(&helper, NULL, chunk_worker, sh) == 0;
+        chunk_worker(sh);
+        if (have_helper) pthread_join(helper, NULL);
+    }
+    pthread_mutex_destroy(&sh->qlock);
+    free(sh->chunk_first);
     return NULL;
 }
 
@@ -126,6 +232,7 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
     Shard shards[MAX_DEV];
     pthread_t threads[MAX_DEV];
     int ndev, devs[MAX_DEV], i, k, nshard = 0, status = 0, *lens = stream_len;
+    const int max_dim = hevce_get_max_dim();   /* one value for the whole call: sharding, clamp and size write-back */
     long long total = 0, acc = 0;
     if (n < 0) return HEVCE_ERR_ARG;
     if (n == 0) return 0;
@@ -134,29 +241,31 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
         if (!pbuffers[i] || !imgs[i] || !img_rcons[i] || ysz[i] <= 0 || xsz[i] <= 0 || qpd6[i] < 0 || qpd6[i] > 4) return HEVCE_ERR_ARG;
     pthread_mutex_lock(&g_lock);
     ndev = resolve_devices();
-    memcpy(devs, g_devs, sizeof(int) * (size_t)(ndev > 0 ? ndev : 0));
+    if (ndev > 0) memcpy(devs, g_devs, sizeof(int) * (size_t)ndev);
     pthread_mutex_unlock(&g_lock);
-    if (ndev <= 0) {
+    if (ndev < 0) return ndev;
+    if (ndev == 0) {
         fprintf(stderr, "libhevce_b200: no usable CUDA device (this library has no CPU path)\n");
         return HEVCE_ERR_CUDA;
     }
     if (!lens) lens = (int *)malloc(sizeof(int) * (size_t)n);
     if (!lens) return HEVCE_ERR_ARG;
-    for (i = 0; i < n; i++) total += padded_pixels(ysz[i], xsz[i]);
+    for (i = 0; i < n; i++) total += padded_pixels(ysz[i], xsz[i], max_dim);
     /* contiguous shards with (nearly) equal padded-pixel = CTU counts */
     if (ndev > n) ndev = n;
+    hevce_internal_set_copy_threads(ndev > 1 ? (ndev >= 8 ? 2 : 8 / ndev) : 0);   /* staging copies: share the host cores between the shards */
     for (k = 0, i = 0; k < ndev; k++) {
         int first = i;
         long long want = total * (k + 1) / ndev;
-        while (i < n && (k == ndev - 1 || acc + padded_pixels(ysz[i], xsz[i]) / 2 <= want)) acc += padded_pixels(ysz[i], xsz[i]), i++;
+        while (i < n && (k == ndev - 1 || acc + padded_pixels(ysz[i], xsz[i], max_dim) / 2 <= want)) acc += padded_pixels(ysz[i], xsz[i], max_dim), i++;
         if (i == first) continue;
-        shards[nshard].device = devs[k]; shards[nshard].first = first; shards[nshard].count = i - first;
+        shards[nshard].device = devs[k]; shards[nshard].first = first; shards[nshard].count = i - first; shards[nshard].max_dim = max_dim;
         shards[nshard].pbuffers = pbuffers; shards[nshard].imgs = imgs; shards[nshard].rcons = img_rcons;
         shards[nshard].ysz = ysz; shards[nshard].xsz = xsz; shards[nshard].qpd6 = qpd6; shards[nshard].stream_len = lens;
         nshard++;
     }
     for (k = 1; k < nshard; k++)
-        if (pthread_create(&threads[k], NULL, shard_main, &shards[k])) { shards[k].status = HEVCE_ERR_CUDA; threads[k] = 0; shard_main(&shards[k]); }
+        if (pthread_create(&threads[k], NULL, shard_main, &shards[k])) { threads[k] = 0; shard_main(&shards[k]); }
     shard_main(&shards[0]);
     for (k = 1; k < nshard; k++)
         if (threads[k]) pthread_join(threads[k], NULL);
@@ -164,8 +273,8 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
         if (shards[k].status && !status) status = shards[k].status;
     if (!status)
         for (i = 0; i < n; i++) {   /* size write-back (HEVCe.c:1643-1644) */
-            ysz[i] = ((ysz[i] < g_max_dim ? ysz[i] : g_max_dim) + 31) / 32 * 32;
-            xsz[i] = ((xsz[i] < g_max_dim ? xsz[i] : g_max_dim) + 31) / 32 * 32;
+            ysz[i] = ((ysz[i] < max_dim ? ysz[i] : max_dim) + 31) / 32 * 32;
+            xsz[i] = ((xsz[i] < max_dim ? xsz[i] : max_dim) + 31) / 32 * 32;
         }
     if (lens != stream_len) free(lens);
     return status;

@@ -49,11 +49,26 @@
 #ifndef HEVCE_OPT_BINSEL
 #define HEVCE_OPT_BINSEL 1
 #endif
+// ---- kernel variant (one translation unit per variant, see hevce_variant.cu): pictures per CTA, threads per picture,
+// trial lanes per warp and the pool plan.  GANG x NT threads run in lock-step phases; WIDE = one picture owns the CTA
+// and most of the SM's shared memory (all 35 candidates of a 16x16 / 32x32 step in one round).
 #ifndef HEVCE_OPT_GANG
 #define HEVCE_OPT_GANG 7
 #endif
+#ifndef HEVCE_OPT_NT
+#define HEVCE_OPT_NT 128
+#endif
+#ifndef HEVCE_OPT_LPW      // trial-coder lanes per warp: 32 = packed (issue-bound gangs), small = spread (latency-bound)
+#define HEVCE_OPT_LPW 32
+#endif
+#ifndef HEVCE_OPT_WIDE
+#define HEVCE_OPT_WIDE 0
+#endif
+#ifndef HEVCE_NS
+#define HEVCE_NS hevce
+#endif
 
-namespace hevce {
+namespace HEVCE_NS {
 
 typedef uint8_t u8;
 typedef int16_t s16;
@@ -63,8 +78,13 @@ typedef uint32_t u32;
 // sizes
 // ------------------------------------------------------------------------------------------------------------
 constexpr int CTU = 32;
-constexpr int NT = 128;            // threads per picture
+constexpr int NT = HEVCE_OPT_NT;   // threads per picture (a multiple of 64)
 constexpr int GANG = HEVCE_OPT_GANG;            // pictures per CTA (lock-step groups of NT threads)
+constexpr int LPW = HEVCE_OPT_LPW;
+constexpr bool WIDE = HEVCE_OPT_WIDE != 0;
+constexpr int NTA = (NT / 2) / 32 * 32, NTB = NT - NTA;   // the two thread teams of a picture on 8x8 nodes: [0, NTA) and [NTA, NT)
+static_assert(NT % 32 == 0 && NTA >= 32 && LPW >= 1 && LPW <= 32, "bad kernel variant");
+constexpr int NTC = 128;           // threads per block of the commit kernel (one CTU each)
 constexpr int NLANE = 70;          // trial-coder lanes with a private context set (the 35 NxN-PU lanes reuse 0..34)
 constexpr int NCAND = 105;         // trial-coder lanes of a CU node: 35 one-TU + 35 four-TU + 35 NxN-PU candidates
 constexpr int NMODE = 35;
@@ -437,8 +457,8 @@ struct Scratch {       // per picture slot, global memory (L2-resident working s
     u8* msz_line;      // CU-size map row of the CTU row above, W/4 entries
 };
 
-constexpr int POOL_BYTES = 18624;
-constexpr int AUX_CODER = 16640;        // pool tail: trial-coder results (free whenever they are used)
+constexpr int POOL_BYTES = WIDE ? 189440 : 18624;
+constexpr int AUX_CODER = WIDE ? 187456 : 16640;   // pool tail: trial-coder results (free whenever they are used)
 
 struct Shared {
     alignas(16) u8 pool[POOL_BYTES];    // per-node carve-up: work blocks, predictions, borders (see Plan<S>)
@@ -470,6 +490,10 @@ struct Shared {
 
 HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CODER); }
 
+// Per-CTA control block behind the picture blocks and the tables: how many picture slots of the gang are live (a short
+// gang leaves slots empty; their threads skip the picture and wait at the CTA barrier of the work queue).
+struct GangCtl { int nlive; int next; };
+
 // The picture's shared-memory block.  Non-inlined functions fetch it through this accessor instead of taking a
 // reference parameter: the compiler then knows the address space and emits LDS/STS instead of generic loads.
 // The constant tables exist once per CTA, behind the GANG picture blocks.
@@ -478,65 +502,101 @@ extern __shared__ __align__(16) unsigned char hevce_smem[];
 __device__ __forceinline__ Shared& my_sm() { return reinterpret_cast<Shared*>(hevce_smem)[threadIdx.x / NT]; }
 __device__ __forceinline__ Tables& my_tb() { return *reinterpret_cast<Tables*>(hevce_smem + GANG * sizeof(Shared)); }
 __device__ __forceinline__ Shared& gang_sm(int p) { return reinterpret_cast<Shared*>(hevce_smem)[p]; }
+__device__ __forceinline__ GangCtl& gang_ctl() { return *reinterpret_cast<GangCtl*>(hevce_smem + GANG * sizeof(Shared) + sizeof(Tables)); }
+__device__ __forceinline__ int gang_live() { return GANG == 1 ? 1 : gang_ctl().nlive; }
 #elif defined(__CUDACC__)
 inline Shared& my_sm() { return *static_cast<Shared*>(nullptr); }   // host pass of nvcc: declared, never executed
 inline Shared& gang_sm(int) { return *static_cast<Shared*>(nullptr); }
 inline Tables& my_tb() { return *static_cast<Tables*>(nullptr); }
+inline GangCtl& gang_ctl() { return *static_cast<GangCtl*>(nullptr); }
+inline int gang_live() { return GANG; }
 #elif defined(HEVCE_SIM_GANG)
 // gang simulator (tests/sim): one host thread per picture of a gang, real barriers between the phases
 extern Shared* g_sim_sms;                                            // GANG picture blocks
 extern Tables* g_sim_tb;
+extern int g_sim_nlive;                                              // live pictures of the gang
 extern thread_local int g_sim_member;                                // this thread's picture slot
 void sim_barrier(int id);                                            // 0: CTA-wide, 1 / 2: the two teams
 inline Shared& my_sm() { return g_sim_sms[g_sim_member]; }
 inline Shared& gang_sm(int p) { return g_sim_sms[p]; }
 inline Tables& my_tb() { return *g_sim_tb; }
+inline int gang_live() { return g_sim_nlive; }
 #else
 extern Shared* g_sim_sm;                                             // CTA simulator (tests/sim)
 extern Tables* g_sim_tb;
 inline Shared& my_sm() { return *g_sim_sm; }
 inline Shared& gang_sm(int) { return *g_sim_sm; }
 inline Tables& my_tb() { return *g_sim_tb; }
+inline int gang_live() { return 1; }
 #endif
 static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail too small");
 
-// work-item phases.  On the GPU a phase is a strided loop over the CTA's threads followed by __syncthreads();
+// ---- thread <-> work mappings (shared by the kernel and the gang simulator) ---------------------------------------
+// Teams: id 0 = all NT threads of a picture, 1 = team A [0, NTA), 2 = team B [NTA, NT).
+HEVCE_HD inline int team_t0(int id) { return id == 2 ? NTA : 0; }
+HEVCE_HD inline int team_size(int id) { return id == 0 ? NT : id == 1 ? NTA : NTB; }
+// first work item of picture thread `tid` in a phase of team `id` whose item 0 sits on team thread `off` (mod team size);
+// n when the thread is not in the team
+HEVCE_HD inline int team_first(int tid, int id, int off, int n) {
+    const int r = tid - team_t0(id);
+    if (id == 0) return (r + NT - off % NT) % NT;
+    if (id == 1) return (unsigned)r < (unsigned)NTA ? (r + NTA - off % NTA) % NTA : n;
+    return (unsigned)r < (unsigned)NTB ? (r + NTB - off % NTB) % NTB : n;
+}
+// Trial-coder lanes: thread x of a linear thread space hosts lane (x/32)*LPW + x%32 when x%32 < LPW (LPW = 32: every
+// thread hosts a lane, lanes packed into full warps; small LPW: few lanes per warp, less divergence per warp).
+HEVCE_HD inline int host_lane(int x) { return (x & 31) < LPW ? (x >> 5) * LPW + (x & 31) : -1; }
+HEVCE_HD inline int lane_capacity(int nthreads) { return (nthreads >> 5) * LPW; }
+HEVCE_HD inline int round_lanes(int n) { return (n + LPW - 1) / LPW * LPW; }   // next warp boundary in lane space
+// team-B threads of the live pictures as one linear space: slot * NTB + (tid - NTA); -1 for team-A threads
+HEVCE_HD inline int upper_index(int slot, int tid) { return tid >= NTA ? slot * NTB + tid - NTA : -1; }
+// Items shared by the team-B threads that host none of the first `nlanes` lanes (whole warps); when every warp hosts a
+// lane all team-B threads share them after their lane.  Returns the first item of linear team-B thread `ub`, sets stride.
+HEVCE_HD inline int upper_free_first(int ub, int nlanes, int nlive, int n, int& stride) {
+    const int nw = nlive * NTB / 32, hostw = imin((nlanes + LPW - 1) / LPW, nw);
+    if (ub < 0) { stride = 1; return n; }
+    if (hostw == nw) { stride = nw * 32; return ub; }
+    stride = (nw - hostw) * 32;
+    return ub >= hostw * 32 ? ub - hostw * 32 : n;
+}
+
+// work-item phases.  On the GPU a phase is a strided loop over the CTA's threads followed by a barrier;
 // in the simulator it is a loop over the items in a permuted order.
 #if defined(__CUDA_ARCH__)
-// A CTA holds GANG pictures of identical size, one per group of NT threads; the groups run the same phases in
-// lock-step (CTA-wide barriers), so every warp of the SM executes the same code at the same time.
-#define HEVCE_TID ((int)(threadIdx.x & (NT - 1)))
+// A CTA holds up to GANG pictures of identical size, one per group of NT threads; the groups run the same phases in
+// lock-step (barriers over the live pictures), so every warp of the SM executes the same code at the same time.
+#define HEVCE_SLOT ((int)(threadIdx.x / NT))
+#define HEVCE_TID ((int)(threadIdx.x % NT))
 #define PAR_FOR(item, n) for (int item = HEVCE_TID; item < (n); item += NT)
-#define PAR_FOR_OFF(item, n, off) for (int item = (HEVCE_TID + NT - ((off) & (NT - 1))) & (NT - 1); item < (n); item += NT)
-// threads [t0, t0 + nthr) of the picture only (nthr a power of two); item 0 starts at thread t0 + off
-#define PAR_FOR_TEAM(item, n, t0, nthr, off) for (int item = (unsigned)(HEVCE_TID - (t0)) < (unsigned)(nthr) ? ((HEVCE_TID - (t0) + (nthr) - ((off) & ((nthr) - 1))) & ((nthr) - 1)) : (n); item < (n); item += (nthr))
-// 8x8 nodes split every picture's threads into two teams of NT/2 that run independent phase chains; a team's barrier
-// spans the same team of all pictures of the gang (their trial lanes are packed across pictures)
-#define TEAM_A if (HEVCE_TID < NT / 2)
+// threads of team `id` of the picture only; item 0 starts at team thread `off`
+#define PAR_FOR_TEAM(item, n, id, off) for (int item = team_first(HEVCE_TID, (id), (off), (n)); item < (n); item += team_size(id))
+// 8x8 nodes split every picture's threads into two teams that run independent phase chains; a team's barrier spans the
+// same team of all live pictures of the gang (their trial lanes are packed across pictures)
+#define TEAM_A if (HEVCE_TID < NTA)
 #define TEAM_B else
 #define TEAM_JOIN() ((void)0)   // the CTA-wide barrier that follows is the join
-#define TEAM_SYNC(id) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(GANG * NT / 2) : "memory")
-// Trial-coder lanes are packed across the pictures of the gang (full warps): lane L of the CTA, or lane u of the
-// "upper half" threads (threads 64..127 of every picture) while the lower halves run phase-D items.
-#define GANG_RT GANG
-#define GANG_FOR(L, n) for (int L = (int)threadIdx.x; L < (n); L += NT * GANG)
-#define GANG_FOR_UPPER(u, n) for (int u = HEVCE_TID >= NT / 2 ? (int)(threadIdx.x / NT) * (NT / 2) + HEVCE_TID - NT / 2 : (n); u < (n); u += GANG * NT / 2)
-// the upper-half threads that GANG_FOR_UPPER(u, first) leaves idle share n items of any picture of the gang
-#define GANG_FOR_UPPER_FREE(it, first, n) for (int it = (HEVCE_TID >= NT / 2 && (int)(threadIdx.x / NT) * (NT / 2) + HEVCE_TID - NT / 2 >= (first)) ? (int)(threadIdx.x / NT) * (NT / 2) + HEVCE_TID - NT / 2 - (first) : (n); it < (n); it += GANG * NT / 2 - (first))
-#define PHASE_END() __syncthreads()
+#define HEVCE_BAR(id, cnt) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(cnt) : "memory")
+#define TEAM_SYNC(id) HEVCE_BAR(id, gang_live() * ((id) == 1 ? NTA : NTB))
+// Trial-coder lanes of all live pictures, hosted by the CTA's threads (GANG_FOR) or by the team-B threads (GANG_FOR_UPPER)
+#define GANG_RT (gang_live())
+#define GANG_FOR(L, n) for (int L = host_lane((int)threadIdx.x), cap_ = lane_capacity(gang_live() * NT); (unsigned)L < (unsigned)(n); L += cap_)
+#define GANG_FOR_UPPER(u, n) for (int u = HEVCE_TID >= NTA ? host_lane(upper_index(HEVCE_SLOT, HEVCE_TID)) : -1, cap_ = lane_capacity(gang_live() * NTB); (unsigned)u < (unsigned)(n); u += cap_)
+// the team-B threads that host none of the `first` lanes share n items of any picture of the gang
+#define GANG_FOR_UPPER_FREE(it, first, n) for (int st_ = 1, it = upper_free_first(upper_index(HEVCE_SLOT, HEVCE_TID), (first), gang_live(), (n), st_); it < (n); it += st_)
+#define PHASE_END() HEVCE_BAR(3, gang_live() * NT)
 // between the pixel phases A..D of one round: all lines of a candidate's TU are work items of the same warp (T <= 32
 // consecutive items, groups start at multiples of T), so the hand-over needs no CTA- or team-wide barrier
 #define WARP_SYNC() __syncwarp()
 #if defined(HEVCE_PROFILE)   // per-phase latency histogram (development builds only)
 extern __device__ unsigned long long g_phase_cycles[128];
 extern __device__ unsigned long long g_phase_count[128];
-#define PHASE_END_T(tag) do { __syncthreads(); if (threadIdx.x == 0) { const long long t_ = clock64(); \
+#define PHASE_END_T(tag) do { PHASE_END(); if (threadIdx.x == 0) { const long long t_ = clock64(); \
     atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - sm.prof_last)); atomicAdd(&g_phase_count[tag], 1ull); sm.prof_last = t_; } } while (0)
 #define TEAM_PROF_BEGIN() long long tp_ = clock64()
 #define TEAM_PROF(tag, lead) do { if (threadIdx.x == (lead)) { const long long t_ = clock64(); \
     atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - tp_)); atomicAdd(&g_phase_count[tag], 1ull); tp_ = t_; } } while (0)
 #else
-#define PHASE_END_T(tag) __syncthreads()
+#define PHASE_END_T(tag) PHASE_END()
 #define TEAM_PROF_BEGIN() ((void)0)
 #define TEAM_PROF(tag, lead) ((void)0)
 #endif
@@ -553,8 +613,7 @@ inline int sim_item(int i, int n) {
     return (int)(((long long)i * a + 7) % n);
 }
 #define PAR_FOR(item, n) for (int item##_i = 0, item = 0; item##_i < (n) && ((item = sim_item(item##_i, (n))), true); item##_i++)
-#define PAR_FOR_OFF(item, n, off) PAR_FOR(item, n)
-#define PAR_FOR_TEAM(item, n, t0, nthr, off) PAR_FOR(item, n)
+#define PAR_FOR_TEAM(item, n, id, off) PAR_FOR(item, n)
 #if defined(HEVCE_SIM_GANG)
 // the two teams of a picture really run side by side: team A on a helper thread, team B on the picture's thread
 #define TEAM_A auto team_a_ = [&](int member_) { g_sim_member = member_;
@@ -570,14 +629,15 @@ inline int sim_item(int i, int n) {
 #define TEAM_PROF(tag, lead) ((void)0)
 #if defined(HEVCE_SIM_GANG)
 // Host thread m stands for the NT threads of picture slot m: it runs the gang-wide loops for exactly the lane / thread
-// indices those threads own on the GPU, so the cross-picture packing and the barrier structure are exercised for real
-// (each thread runs its team A section, then its team B section; the team barriers span the threads).
-#define GANG_RT GANG
-#define GANG_FOR(L, n) for (int L = g_sim_member * NT; L < (n) && L < (g_sim_member + 1) * NT; L++)
-#define GANG_FOR_UPPER(u, n) for (int u = g_sim_member * (NT / 2); u < (n) && u < (g_sim_member + 1) * (NT / 2); u++)
-#define GANG_FOR_UPPER_FREE(it, first, n) \
-    for (int u_ = g_sim_member * (NT / 2) > (first) ? g_sim_member * (NT / 2) : (first); u_ < (g_sim_member + 1) * (NT / 2); u_++) \
-        for (int it = u_ - (first); it < (n); it += GANG * NT / 2 - (first))
+// indices those threads own on the GPU (same mapping functions), so the cross-picture packing and the barrier structure
+// are exercised for real (each thread runs its team A section, then its team B section; the team barriers span the threads).
+#define GANG_RT (gang_live())
+#define GANG_FOR(L, n) for (int x_ = g_sim_member * NT; x_ < (g_sim_member + 1) * NT; x_++) \
+    for (int L = host_lane(x_), cap_ = lane_capacity(gang_live() * NT); (unsigned)L < (unsigned)(n); L += cap_)
+#define GANG_FOR_UPPER(u, n) for (int x_ = NTA; x_ < NT; x_++) \
+    for (int u = host_lane(upper_index(g_sim_member, x_)), cap_ = lane_capacity(gang_live() * NTB); (unsigned)u < (unsigned)(n); u += cap_)
+#define GANG_FOR_UPPER_FREE(it, first, n) for (int x_ = NTA; x_ < NT; x_++) \
+    for (int st_ = 1, it = upper_free_first(upper_index(g_sim_member, x_), (first), gang_live(), (n), st_); it < (n); it += st_)
 #define TEAM_SYNC(id) sim_barrier(id)
 #define PHASE_END() sim_barrier(0)
 #define PHASE_END_T(tag) sim_barrier(0)
@@ -808,7 +868,7 @@ HEVCE_HD inline void put_residual(BAC& b, const Tables& tbl, const Cx cx, int s,
 // in its own small shared block.  Both are reached through the extern shared array so the accesses stay LDS/STS.
 struct CommitShared {
     Tables tb;
-    u32 ctx[CTXW * NT];   // lane-private context sets of the NT commit threads of a block, word-interleaved
+    u32 ctx[CTXW * NTC];  // lane-private context sets of the NTC commit threads of a block, word-interleaved
 };
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ CommitShared& my_csm() { return *reinterpret_cast<CommitShared*>(hevce_smem); }
@@ -1196,16 +1256,16 @@ HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, i
 }
 
 // phase runners: one (non-inlined) copy per TU size, shared by all node sizes
-struct Team { int t0, nthr; };   // the threads of a picture that share a phase: [t0, t0 + nthr)
+typedef int Team;   // team id of a phase: 0 = all threads of the picture, 1 = team A, 2 = team B (team_first / team_size)
 template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_borders(const Grp& gref, int off, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
     if (g.n == 0) return;
-    if (!g.priv) { PAR_FOR_TEAM(j, 4 * T + 1, tm.t0, tm.nthr, off) border_column<T>(sm, g, j, 0, 0); }
+    if (!g.priv) { PAR_FOR_TEAM(j, 4 * T + 1, tm, off) border_column<T>(sm, g, j, 0, 0); }
     else {   // private neighbours: the candidate loop of one border index is shared by four work items
         const int per = (g.n + 3) >> 2;
-        PAR_FOR_TEAM(it, 4 * (4 * T + 1), tm.t0, tm.nthr, off) {
+        PAR_FOR_TEAM(it, 4 * (4 * T + 1), tm, off) {
             const int j = it >> 2, c0 = (it & 3) * per;
             border_column<T>(sm, g, j, c0, imin(g.n, c0 + per));
         }
@@ -1215,28 +1275,28 @@ template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_phase_a(const Grp& gref, int off, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;
-    PAR_FOR_TEAM(item, g.n * T, tm.t0, tm.nthr, off) phase_a_item<T>(sm, g, item);
+    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_a_item<T>(sm, g, item);
 }
 template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_phase_b(const Grp& gref, int off, int q, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;
     const RdK rk = rd_consts(q);
-    PAR_FOR_TEAM(item, g.n * T, tm.t0, tm.nthr, off) phase_b_item<T>(sm, g, item, q, rk);
+    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_b_item<T>(sm, g, item, q, rk);
 }
 template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_phase_c(const Scratch& scref, const Grp& gref, int off, int q, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;
     const Scratch sc = scref;
-    PAR_FOR_TEAM(item, g.n * T, tm.t0, tm.nthr, off) phase_c_item<T>(sm, sc, g, item, q);
+    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_c_item<T>(sm, sc, g, item, q);
 }
 template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, int off, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;
     const Scratch sc = scref;
-    PAR_FOR_TEAM(item, g.n * T, tm.t0, tm.nthr, off) phase_d_item<T>(sm, sc, g, item);
+    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_d_item<T>(sm, sc, g, item);
 }
 // phase D of a group for every picture of the gang, on the upper-half threads that host no trial lane
 template <int T>
@@ -1255,13 +1315,22 @@ HEVCE_HD HEVCE_NOINLINE void run_phase_d_free(const Grp& gref, int first) {
 // candidates (T = S/2), group 2 (S = 8 only) = NxN PU candidates (T = 4)
 template <int S> struct Plan {
     static constexpr int H = S / 2;
-    // 32x32 nodes run in two stages that reuse the pool: R0 one-TU rounds of 4 candidates (128 line items of T = 32: one
-    // full pass), then 3 chunks of 12 four-TU candidates x 4 sub-TUs.  Mixing both in one round left the 64 threads
-    // without a 32-point line idle most of the time.
-    static constexpr int N0 = S == 8 ? 35 : S == 16 ? 6 : 4;     // one-TU candidates per round
-    static constexpr int N1 = S == 32 ? 12 : 35;                 // four-TU candidates per chunk
-    static constexpr int R0 = S == 32 ? 9 : 0;                   // 32: one-TU-only rounds that come first
-    static constexpr int ROUNDS = S == 32 ? R0 + 12 : S == 16 ? 6 : 4; // 16: 4 sub-TU rounds + 2 one-TU-only
+    // Gang variants (18 KB pool per picture): 16x16 nodes take the one-TU candidates 6 per round beside the four sub-TU
+    // rounds; 32x32 nodes run in two stages that reuse the pool: R0 one-TU rounds of 4 candidates (128 line items of
+    // T = 32: one full pass), then 3 chunks of 12 four-TU candidates x 4 sub-TUs.
+    // Wide variant (one picture per CTA, 185 KB pool): all 35 one-TU candidates in round 0 beside sub-TU 0 of all 35
+    // four-TU candidates, then sub-TUs 1..3: four rounds for every node size.
+    static constexpr int N0 = (S == 8 || WIDE) ? 35 : S == 16 ? 6 : 4;     // one-TU candidates per round
+    static constexpr int N1 = (S == 32 && !WIDE) ? 12 : 35;                // four-TU candidates per chunk
+    static constexpr int R0 = (S == 32 && !WIDE) ? 9 : 0;                  // gang 32x32: one-TU-only rounds that come first
+    static constexpr int ROUNDS = WIDE ? 4 : S == 32 ? R0 + 12 : S == 16 ? 6 : 4; // gang 16x16: 4 sub-TU rounds + 2 one-TU-only
+    static constexpr bool OVERLAY = S == 32 && !WIDE;                      // group 1 reuses group 0's pool space
+    // round r: one-TU candidates [g0_m0, g0_m0 + g0_n), four-TU candidates [g1_m0, g1_m0 + g1_n) at sub-TU g1_tu
+    static HEVCE_HD int g0_m0(int r) { return r * N0; }
+    static HEVCE_HD int g0_n(int r) { return (r < 0 || (OVERLAY && r >= R0)) ? 0 : imax(0, imin(N0, NMODE - r * N0)); }
+    static HEVCE_HD int g1_tu(int r) { return (r - R0) & 3; }
+    static HEVCE_HD int g1_m0(int r) { return ((r - R0) >> 2) * N1; }
+    static HEVCE_HD int g1_n(int r) { return r < R0 ? 0 : imax(0, imin(N1, NMODE - g1_m0(r))); }
     static constexpr int al(int v) { return (v + 15) & ~15; }
     // group 0
     static constexpr int BLK0 = 0;
@@ -1270,7 +1339,7 @@ template <int S> struct Plan {
     static constexpr int BORD0 = PSUM0 + al(N0 * S * S);         // S*S/4 ints
     static constexpr int END0 = BORD0 + al(2 * Dim<S>::BS);
     // group 1
-    static constexpr int BLK1 = S == 32 ? 0 : END0;
+    static constexpr int BLK1 = OVERLAY ? 0 : END0;
     static constexpr int PRED1 = BLK1 + al(N1 * Dim<H>::BLK * 2);
     static constexpr int PSUM1 = PRED1 + al(N1 * H * H);
     static constexpr int BORD1 = PSUM1 + al(N1 * H * H);
@@ -1283,7 +1352,7 @@ template <int S> struct Plan {
     static constexpr int BORD2 = PSUM2 + al(35 * 16);
     static constexpr int REC2 = BORD2 + al(2 * Dim<4>::BS);
     static constexpr int END2 = REC2 + al(35 * 16);
-    static constexpr int TOTAL = S == 8 ? END2 : S == 32 ? (END0 > END1 ? END0 : END1) : END1;
+    static constexpr int TOTAL = S == 8 ? END2 : OVERLAY ? (END0 > END1 ? END0 : END1) : END1;
     static_assert(TOTAL <= POOL_BYTES, "shared-memory pool too small");
     static_assert(S != 8 || TOTAL <= AUX_CODER, "8x8 pipeline buffers overlap the trial-coder results");
 };
@@ -1385,9 +1454,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
     // ---- group descriptors (uniform over the threads of a picture)
     auto group0 = [&](int r) -> Grp {   // one-TU candidates: a slice of the 35 modes per round
         Grp g;
-        int m0, n;
-        if (S == 8) { m0 = 0; n = r == 0 ? 35 : 0; }
-        else { m0 = r * P::N0; n = (S == 32 && r >= P::R0) ? 0 : imax(0, imin(P::N0, NMODE - m0)); }
+        const int m0 = P::g0_m0(r), n = P::g0_n(r);
         g.n = n; g.cand0 = m0; g.mode0 = m0; g.ty = y0; g.tx = x0; g.av = av; g.priv = 0;
         g.cuy = y0; g.cux = x0; g.cus = S; g.tu = 0; g.one_tu = 1; g.grec = 1;
         g.blk = P::BLK0; g.pred = P::PRED0; g.psum = P::PSUM0; g.bord = P::BORD0;
@@ -1396,8 +1463,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
     };
     auto group1 = [&](int r) -> Grp {   // four-TU candidates: sub-TU k of a chunk of modes, each with its own reconstruction as neighbour
         Grp g;
-        const int rr = r - P::R0, k = rr & 3, chunk = rr >> 2;   // 32x32 nodes only: chunks of four-TU modes
-        const int m0 = chunk * P::N1, n = ((S == 16 && r >= 4) || rr < 0) ? 0 : imax(0, imin(P::N1, NMODE - m0));
+        const int k = P::g1_tu(r), m0 = P::g1_m0(r), n = P::g1_n(r);
         g.n = n; g.cand0 = NMODE + m0; g.mode0 = m0; g.ty = y0 + (k >> 1) * H; g.tx = x0 + (k & 1) * H; g.av = sub_avail(av, k); g.priv = 1;
         g.cuy = y0; g.cux = x0; g.cus = S; g.tu = k; g.one_tu = 0; g.grec = 1;
         g.blk = P::BLK1; g.pred = P::PRED1; g.psum = P::PSUM1; g.bord = P::BORD1;
@@ -1414,7 +1480,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
     };
 
     if constexpr (S > 8) {
-        const Team all = {0, NT};
+        const Team all = 0;
         for (int r = 0; r < P::ROUNDS; r++) {
             const Grp g0 = group0(r), g1 = group1(r);
             const int i0 = g0.n * S;
@@ -1441,7 +1507,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
         // four-TU candidates; team B (upper half) walks the four NxN PUs, whose CABAC lanes are the long pole.  Team A
         // reads the window outside the CU only and team B writes it inside the CU only, so the chains meet at the end.
         TEAM_A {
-            const Team ta = {0, NT / 2};
+            const Team ta = 1;
             TEAM_PROF_BEGIN();
             for (int r = 0; r < 4; r++) {
                 const Grp g0 = group0(r), g1 = group1(r);
@@ -1465,7 +1531,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             }
         }
         TEAM_B {
-            const Team tb = {NT / 2, NT / 2};
+            const Team tb = 2;
             TEAM_PROF_BEGIN();
             for (int k = 0; k < 4; k++) {
                 const Grp g2 = group2(k);
@@ -1477,7 +1543,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
                 WARP_SYNC();
                 run_phase_c<4>(sc, g2, 0, q, tb);
                 TEAM_SYNC(2);
-                TEAM_PROF(P_TB_PIX, NT / 2);
+                TEAM_PROF(P_TB_PIX, NTA);
                 // NxN PU coders of this PU, all pictures of the gang, packed into full warps; the threads left over
                 // reconstruct the candidates meanwhile (phase D of any picture of the gang)
                 GANG_FOR_UPPER(u, GANG_RT * NMODE) {
@@ -1486,10 +1552,10 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
                 }
                 run_phase_d_free<4>(g2, GANG_RT * NMODE);
                 TEAM_SYNC(2);
-                TEAM_PROF(P_TB_CABAC, NT / 2);
-                PAR_FOR_TEAM(m, NMODE, NT / 2, NT / 2, 0) sm.cand_bits[2 * NMODE + m] = rd_cost(rk, sm.cand_sse[2 * NMODE + m], sm.cand_bits[2 * NMODE + m]);
+                TEAM_PROF(P_TB_CABAC, NTA);
+                PAR_FOR_TEAM(m, NMODE, 2, 0) sm.cand_bits[2 * NMODE + m] = rd_cost(rk, sm.cand_sse[2 * NMODE + m], sm.cand_bits[2 * NMODE + m]);
                 TEAM_SYNC(2);
-                PAR_FOR_TEAM(i, 16, NT / 2, NT / 2, 0) {   // best PU mode, last minimum wins (HEVCe.c:1521); one sample per thread
+                PAR_FOR_TEAM(i, 16, 2, 0) {   // best PU mode, last minimum wins (HEVCe.c:1521); one sample per thread
                     int best = IMAX, bm = 0;
                     for (int m = 0; m < NMODE; m++) {
                         const int c = sm.cand_bits[2 * NMODE + m];
@@ -1501,7 +1567,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
                     HEVCE_WIN(sm, g2.ty + (i >> 2), g2.tx + (i & 3)) = sm.pool[g2.rec + bm * 16 + i];
                 }
                 TEAM_SYNC(2);
-                TEAM_PROF(P_TB_ARGMIN, NT / 2);
+                TEAM_PROF(P_TB_ARGMIN, NTA);
             }
         }
         TEAM_JOIN();
@@ -1511,11 +1577,11 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
     // ---- all one-TU / four-TU trial coders of the gang (70 per picture), packed step-major into full warps; for 8x8
     // nodes one more lane per picture codes the NxN CU as a whole
     {
-        constexpr int NC = GANG_RT * NMODE;
+        const int NC = GANG_RT * NMODE;
 #if defined(HEVCE_PROFILE) && defined(__CUDA_ARCH__)
         const long long tw0_ = clock64();
 #endif
-        constexpr int NCP = (NC + 31) & ~31;   // every step starts on a warp boundary: one-TU, four-TU and NxN lanes run
+        const int NCP = round_lanes(NC);       // every step starts on a warp boundary: one-TU, four-TU and NxN lanes run
                                                // different code and would serialise inside a shared warp
         GANG_FOR(L, 2 * NCP + (S == 8 ? GANG_RT : 0)) {
             if (L < 2 * NCP) {
@@ -1635,8 +1701,8 @@ HEVCE_HD inline void commit_ctu(const Job& job, int ctu, int lane) {
     const CtuRec& r = job.recs[ctu];
     const s16* lev = job.levs + (size_t)ctu * (CTU * CTU);
     u32* cw = cs.ctx + lane;
-    for (int k = 0; k < CTXW; k++) cw[k * NT] = ((const u32*)r.ctx)[k];
-    const int cx_off = (int)((u8*)cw - (u8*)&cs), cx_s4 = 4 * NT;
+    for (int k = 0; k < CTXW; k++) cw[k * NTC] = ((const u32*)r.ctx)[k];
+    const int cx_off = (int)((u8*)cw - (u8*)&cs), cx_s4 = 4 * NTC;
     const Cx cx = {(u8*)cw, cx_s4};
     BacCommit b;
     b.c = r.start;
@@ -1663,7 +1729,7 @@ HEVCE_HD inline void commit_ctu(const Job& job, int ctu, int lane) {
     if (!coder_equal(b.c, r.end)) err |= ERR_COMMIT_MISMATCH;   // the adopted trial state must be what the bytes produce
     if (!r.last) {
         const u32* nx = (const u32*)job.recs[ctu + 1].ctx;
-        for (int k = 0; k < CTXW; k++) if (cw[k * NT] != nx[k]) err |= ERR_COMMIT_MISMATCH;
+        for (int k = 0; k < CTXW; k++) if (cw[k * NTC] != nx[k]) err |= ERR_COMMIT_MISMATCH;
     }
     if (b.c.n > b.cap) err |= ERR_OVERFLOW;
     if (err) HEVCE_ATOMIC_OR(job.result + 1, err);
@@ -1709,7 +1775,7 @@ HEVCE_HD inline int write_header(u8* out, int q, int H, int W) {
 // ------------------------------------------------------------------------------------------------------------
 // one picture (HEVCe.c:1570-1647)
 // ------------------------------------------------------------------------------------------------------------
-HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared& sm, const Scratch& sc) {
+HEVCE_HD inline void encode_picture(const Job& job, Shared& sm, const Scratch& sc) {
     const int q = job.q, H = job.H, W = job.W;
     PAR_FOR(i, 4 * CTXW) {
         const u8 v = ctx_init_value(my_tb().ctx_iv[i], q);
@@ -1794,4 +1860,4 @@ HEVCE_HD inline void encode_picture(const Job& job, const Tables& tables, Shared
     PHASE_END_T(P_MISC);
 }
 
-}   // namespace hevce
+}   // namespace HEVCE_NS

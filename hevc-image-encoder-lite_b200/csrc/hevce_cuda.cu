@@ -1,8 +1,8 @@
 // hevce_cuda.cu -- sm_100a kernels + device-resident sessions of libhevce_b200.so.
 //
-// Kernel: hevce_encode_kernel -- a persistent grid of 128-thread CTAs; every CTA pulls pictures from a queue
-// (largest first) and encodes each one completely (hevce_core.h: encode_picture).  Pictures are independent, so the
-// grid needs no inter-CTA communication; the batch is the parallel axis.
+// The decision kernel (hevce_core.h: encode_picture) is linked in several variants (hevce_variant.cu, hevce_variants.h):
+// gangs of 7 / 4 / 2 pictures per CTA and one "wide" picture per CTA.  This file picks the variant per batch, owns the
+// commit / quality / peak kernels and everything between the plain-C API (hevce_api.c) and the device.
 //
 // Host side here is the thin layer between the plain-C API (hevce_api.c) and the device: buffer management in HBM,
 // pinned staging, launches, CUDA-event timing.  No CPU implementation of any encoder stage exists in this library.
@@ -21,6 +21,7 @@
 #include "../../include/hevce.h"
 #include "hevce_core.h"
 #include "hevce_internal.h"
+#include "hevce_variants.h"
 
 using namespace hevce;
 
@@ -36,42 +37,25 @@ using namespace hevce;
 // ------------------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------------------
-__device__ Tables g_tables;
-#if defined(HEVCE_PROFILE)
-namespace hevce {
-__device__ unsigned long long g_phase_cycles[128];
-__device__ unsigned long long g_phase_count[128];
-}
-#endif
-
-// A CTA = GANG pictures of identical padded size, one per group of NT threads.  `gangs` lists GANG job indices per
-// work unit (a short gang repeats its first job: the duplicate writes identical bytes).
-__global__ void __launch_bounds__(NT * GANG, (6 % GANG == 0) ? 6 / GANG : 1)
-hevce_encode_kernel(const Job* __restrict__ jobs, const int* __restrict__ gangs, int ngangs, const Scratch* __restrict__ slots, int* counter) {
-    const int member = threadIdx.x / NT;
-    Shared& sm = my_sm();
-    __shared__ int s_next;
-    const Scratch sc = slots[blockIdx.x * GANG + member];
-    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += NT * GANG) ((u32*)&my_tb())[i] = ((const u32*)&g_tables)[i];
-    for (;;) {
-        if (threadIdx.x == 0) s_next = atomicAdd(counter, 1);
-        __syncthreads();
-        const int k = s_next;
-        __syncthreads();
-        if (k >= ngangs) break;
-        const Job job = jobs[gangs[k * GANG + member]];
-        encode_picture(job, g_tables, sm, sc);
-    }
-}
-
 // Commit pass: one thread per CTU re-encodes the decided CTU with the byte-writing coder.  blockIdx.y = picture.
-__global__ void __launch_bounds__(NT) hevce_commit_kernel(const Job* __restrict__ jobs) {
+__global__ void __launch_bounds__(NTC) hevce_commit_kernel(const Job* __restrict__ jobs, const Tables* __restrict__ tables) {
     CommitShared& cs = my_csm();
-    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += NT) ((u32*)&cs.tb)[i] = ((const u32*)&g_tables)[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += NTC) ((u32*)&cs.tb)[i] = ((const u32*)tables)[i];
     __syncthreads();
     const Job job = jobs[blockIdx.y];
-    const int nctu = (job.H / CTU) * (job.W / CTU), ctu = blockIdx.x * NT + threadIdx.x;
+    const int nctu = (job.H / CTU) * (job.W / CTU), ctu = blockIdx.x * NTC + threadIdx.x;
     if (ctu < nctu) commit_ctu(job, ctu, threadIdx.x);
+}
+
+// Stream gather: the streams of a batch lie in per-picture slots of worst-case size; this copies each one to its
+// 16-byte-aligned place in one contiguous buffer so the host needs a single device-to-host copy.  blockIdx.x = picture.
+__global__ void __launch_bounds__(256) hevce_pack_kernel(const Job* __restrict__ jobs, const unsigned long long* __restrict__ dst_off,
+                                                         const int* __restrict__ results, u8* __restrict__ dst) {
+    const Job job = jobs[blockIdx.x];
+    const int len = min(max(results[2 * blockIdx.x], 0), job.out_cap);
+    const uint4* src = (const uint4*)job.out;               // stream slots start at multiples of 256 bytes
+    uint4* out = (uint4*)(dst + dst_off[blockIdx.x]);
+    for (int i = threadIdx.x; i < (len + 15) / 16; i += blockDim.x) out[i] = src[i];
 }
 
 // Quality pass (HEVCeMain.c:116-133): sum of squared differences between source and reconstruction over the area both
@@ -123,9 +107,42 @@ __global__ void __launch_bounds__(256) hevce_int_peak_kernel(int iters, int seed
 // ------------------------------------------------------------------------------------------------------------
 namespace {
 
+struct Variant {
+    const char* name;
+    int (*prepare)(void);
+    int (*launch)(const void*, const int*, int, const void*, int*, const void*, int, void*);
+    void (*info)(hevce_variant_info*);
+    void (*profile)(unsigned long long*, unsigned long long*);
+    hevce_variant_info vi;
+    double cost;   // relative time per CTU of one gang when the whole GPU runs this variant (measured)
+};
+#if defined(HEVCE_PROFILE_DUMP)
+#define HEVCE_VARIANT_ROW(tag, g, nt, lpw, wide) {#tag, hevce_variant_prepare_##tag, hevce_variant_launch_##tag, hevce_variant_info_##tag, hevce_variant_profile_##tag, {}, 0.0},
+#else
+#define HEVCE_VARIANT_ROW(tag, g, nt, lpw, wide) {#tag, hevce_variant_prepare_##tag, hevce_variant_launch_##tag, hevce_variant_info_##tag, nullptr, {}, 0.0},
+#endif
+Variant g_variants[] = {HEVCE_VARIANT_LIST(HEVCE_VARIANT_ROW)};
+constexpr int NVARIANT = (int)(sizeof(g_variants) / sizeof(g_variants[0]));
+int g_forced_variant = -1;     // hevce_set_variant / HEVCE_VARIANT: -1 = choose per batch
+int g_last_variant = 0;
+
+Tables g_host_tables;
+std::once_flag g_variants_once;
+void variants_init() {
+    std::call_once(g_variants_once, [] {
+        fill_tables(g_host_tables);
+        // relative per-CTU latency of a gang (all SMs busy with the same variant), measured on B200 -- profiles/r2_notes.md
+        static const double kCost[NVARIANT] = {1.00, 0.62, 0.42, 0.30};
+        for (int v = 0; v < NVARIANT; v++) { g_variants[v].info(&g_variants[v].vi); g_variants[v].cost = kCost[v]; }
+        if (const char* env = getenv("HEVCE_VARIANT"))
+            for (int v = 0; v < NVARIANT; v++) if (!strcmp(env, g_variants[v].name)) g_forced_variant = v;
+    });
+}
+
 struct DeviceInfo {
     bool ready = false;
-    int sms = 0, ctas_per_sm = 0;
+    int sms = 0;
+    Tables* d_tables = nullptr;
 };
 std::mutex g_dev_mutex;
 DeviceInfo g_dev[64];
@@ -137,21 +154,40 @@ int device_prepare(int device) {
     if (g_dev[device].ready) return 0;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
+    if (prop.major != 10 || prop.minor != 0) {   // the cubins are sm_100a: they load on compute capability 10.0 only
         fprintf(stderr, "libhevce_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor);
         return HEVCE_ERR_CUDA;
     }
-    static Tables host_tables;
-    fill_tables(host_tables);
-    CK(cudaMemcpyToSymbol(g_tables, &host_tables, sizeof(Tables)));
-    int occ = 0;
-    CK(cudaFuncSetAttribute(hevce_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GANG * sizeof(Shared) + sizeof(Tables))));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevce_encode_kernel, NT * GANG, GANG * sizeof(Shared) + sizeof(Tables)));
-    if (occ < 1) occ = 1;
+    variants_init();
+    for (int v = 0; v < NVARIANT; v++) CK((cudaError_t)g_variants[v].prepare());
+    CK(cudaMalloc((void**)&g_dev[device].d_tables, sizeof(Tables)));
+    CK(cudaMemcpy(g_dev[device].d_tables, &g_host_tables, sizeof(Tables), cudaMemcpyHostToDevice));
     g_dev[device].sms = prop.multiProcessorCount;
-    g_dev[device].ctas_per_sm = occ;
     g_dev[device].ready = true;
     return 0;
+}
+
+// Work units of a batch for a variant with `gang` pictures per CTA: same-size pictures in order of decreasing size,
+// -1 in the empty slots of a short gang.  Returns the longest-processing-time-first makespan over `bins` CTAs in CTUs.
+long long build_gangs(const std::vector<Job>& jobs, const std::vector<int>& order, int gang, int bins, std::vector<int>* out) {
+    const int n = (int)order.size();
+    std::vector<long long> load((size_t)std::max(1, bins), 0);   // min-heap by load
+    auto cmp = [](long long a, long long b) { return a > b; };
+    long long makespan = 0;
+    if (out) out->clear();
+    for (int i = 0; i < n;) {
+        const Job& f = jobs[order[i]];
+        int m = 1;
+        while (m < gang && i + m < n && jobs[order[i + m]].H == f.H && jobs[order[i + m]].W == f.W) m++;
+        if (out)
+            for (int k = 0; k < gang; k++) out->push_back(k < m ? order[i + k] : -1);
+        std::pop_heap(load.begin(), load.end(), cmp);
+        load.back() += (long long)(f.H / CTU) * (f.W / CTU);
+        makespan = std::max(makespan, load.back());
+        std::push_heap(load.begin(), load.end(), cmp);
+        i += m;
+    }
+    return makespan;
 }
 
 template <class T>
@@ -169,7 +205,7 @@ int grow(T** p, size_t* cap, size_t need) {   // grow-only device buffer
 }   // namespace
 
 struct hevce_session {
-    int device = 0, n = 0, grid = 0, launches = 0, ngangs = 0;
+    int device = 0, n = 0, grid = 0, launches = 0, ngangs = 0, variant = 0;
     float kernel_ms = 0.f, commit_ms = 0.f;
     int max_nctu = 0;
     long long h2d = 0, d2h = 0;
@@ -191,6 +227,8 @@ struct hevce_session {
     size_t c_glev = 0, c_lev = 0, c_grec = 0, c_line = 0;
     CtuRec* d_recs = nullptr; size_t c_recs = 0;
     unsigned long long* d_sse = nullptr; size_t c_sse = 0;
+    u8* d_pack = nullptr; size_t c_pack = 0;
+    unsigned long long* d_packoff = nullptr; size_t c_packoff = 0;
     float quality_ms = 0.f;
     bool encoded = false;   // hevce_session_encode has run since the last configure/upload
     std::vector<size_t> ctu_off;
@@ -201,9 +239,14 @@ struct hevce_session {
 
 // host-side staging copies (user buffers <-> pinned memory) spread over a few threads: at 100 Mpixel/s a single
 // thread's memcpy of a 0.8 GB step is a visible part of the end-to-end time
+static int g_copy_threads = 0;   // 0 = derive from the host's core count
+extern "C" void hevce_internal_set_copy_threads(int n) { g_copy_threads = n; }
+extern "C" int hevce_internal_get_device(void) { int d = -1; return cudaGetDevice(&d) == cudaSuccess ? d : -1; }
+extern "C" void hevce_internal_set_device(int device) { if (device >= 0) cudaSetDevice(device); }
+
 template <class F>
 static void parallel_pictures(int n, size_t total_bytes, F&& fn) {
-    unsigned nt = std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    unsigned nt = g_copy_threads > 0 ? (unsigned)g_copy_threads : std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
     if (total_bytes < ((size_t)16 << 20) || n < 2 * (int)nt) nt = 1;
     if (nt == 1) { for (int i = 0; i < n; i++) fn(i); return; }
     std::vector<std::thread> th;
@@ -222,11 +265,10 @@ static int stage_reserve(hevce_session* s, size_t need) {
     return 0;
 }
 
-extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, const int* xsz, const int* qpd6) {
+extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, const int* xsz, const int* qpd6, int max_dim) {
     if (!s || n < 0 || n > 65535 || (n > 0 && (!ysz || !xsz || !qpd6))) return HEVCE_ERR_ARG;   // grid.y of the commit kernel = picture index
     int rc = device_prepare(s->device);
     if (rc) return rc;
-    const int max_dim = hevce_internal_max_dim();
     s->encoded = false;
     s->n = n;
     s->jobs.assign(n, Job());
@@ -254,7 +296,8 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     }
     s->img_total = io; s->rcon_total = ro; s->out_total = oo;
     if (n == 0) return 0;
-    // work units: gangs of GANG pictures with identical padded size, largest pictures first
+    // work units: gangs of same-size pictures, largest pictures first; the variant (pictures per CTA) that finishes the
+    // batch soonest by the longest-processing-time estimate: makespan in CTUs x the variant's time per CTU
     s->order.resize(n);
     std::iota(s->order.begin(), s->order.end(), 0);
     std::stable_sort(s->order.begin(), s->order.end(), [&](int a, int b) {
@@ -264,17 +307,21 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
         if (x.H != y.H) return x.H > y.H;
         return false;
     });
-    std::vector<int> gangs;
-    for (int i = 0; i < n;) {
-        const Job& f = s->jobs[s->order[i]];
-        int m = 1;
-        while (m < GANG && i + m < n && s->jobs[s->order[i + m]].H == f.H && s->jobs[s->order[i + m]].W == f.W) m++;
-        for (int k = 0; k < GANG; k++) gangs.push_back(s->order[i + (k < m ? k : 0)]);
-        i += m;
-    }
-    s->ngangs = (int)gangs.size() / GANG;
     const DeviceInfo& di = g_dev[s->device];
-    s->grid = std::min(s->ngangs, di.sms * di.ctas_per_sm);
+    int best = g_forced_variant;
+    if (best < 0) {
+        double best_t = 0;
+        for (int v = 0; v < NVARIANT; v++) {
+            const double t = (double)build_gangs(s->jobs, s->order, g_variants[v].vi.gang, di.sms, nullptr) * g_variants[v].cost;
+            if (best < 0 || t < best_t) { best = v; best_t = t; }
+        }
+    }
+    s->variant = best;
+    const int GANGV = g_variants[best].vi.gang;
+    std::vector<int> gangs;
+    build_gangs(s->jobs, s->order, GANGV, di.sms, &gangs);
+    s->ngangs = (int)gangs.size() / GANGV;
+    s->grid = std::min(s->ngangs, di.sms);
     if ((rc = grow(&s->d_img, &s->c_img, io))) return rc;
     if ((rc = grow(&s->d_rcon, &s->c_rcon, ro))) return rc;
     if ((rc = grow(&s->d_out, &s->c_out, oo))) return rc;
@@ -282,7 +329,7 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     if ((rc = grow(&s->d_order, &s->c_order, gangs.size()))) return rc;
     if ((rc = grow(&s->d_results, &s->c_results, (size_t)2 * n))) return rc;
     if (!s->d_counter) CK(cudaMalloc((void**)&s->d_counter, sizeof(int)));
-    const size_t g = (size_t)s->grid * GANG, nlev = (size_t)NCAND * LEV_STRIDE + 64, nrec = (size_t)NREC * CTU * CTU;
+    const size_t g = (size_t)s->grid * GANGV, nlev = (size_t)NCAND * LEV_STRIDE + 64, nrec = (size_t)NREC * CTU * CTU;
     s->line_pitch = maxW / 4 + 32;
     if ((rc = grow(&s->d_glev, &s->c_glev, g * nlev))) return rc;
     if ((rc = grow(&s->d_grec, &s->c_grec, g * nrec))) return rc;
@@ -312,7 +359,7 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     return 0;
 }
 
-extern "C" hevce_session* hevce_session_create(int device, int n, const int* ysz, const int* xsz, const int* qpd6) {
+extern "C" hevce_session* hevce_session_create_empty(int device) {
     if (device_prepare(device)) return nullptr;
     hevce_session* s = new hevce_session;
     s->device = device;
@@ -322,7 +369,12 @@ extern "C" hevce_session* hevce_session_create(int device, int n, const int* ysz
         hevce_session_destroy(s);
         return nullptr;
     }
-    if (hevce_session_configure(s, n, ysz, xsz, qpd6)) { hevce_session_destroy(s); return nullptr; }
+    return s;
+}
+
+extern "C" hevce_session* hevce_session_create(int device, int n, const int* ysz, const int* xsz, const int* qpd6) {
+    hevce_session* s = hevce_session_create_empty(device);
+    if (s && hevce_session_configure(s, n, ysz, xsz, qpd6, hevce_internal_max_dim())) { hevce_session_destroy(s); return nullptr; }
     return s;
 }
 
@@ -352,12 +404,12 @@ extern "C" int hevce_session_encode(hevce_session* s) {
     CK(cudaMemsetAsync(s->d_counter, 0, sizeof(int), s->stream));
     CK(cudaMemsetAsync(s->d_results, 0, 2 * (size_t)s->n * sizeof(int), s->stream));
     CK(cudaEventRecord(s->ev0, s->stream));
-    hevce_encode_kernel<<<s->grid, NT * GANG, GANG * sizeof(Shared) + sizeof(Tables), s->stream>>>(s->d_jobs, s->d_order, s->ngangs, s->d_slots, s->d_counter);
-    CK(cudaGetLastError());
+    CK((cudaError_t)g_variants[s->variant].launch(s->d_jobs, s->d_order, s->ngangs, s->d_slots, s->d_counter, g_dev[s->device].d_tables, s->grid, s->stream));
+    g_last_variant = s->variant;
     CK(cudaEventRecord(s->ev1, s->stream));
     {
-        const dim3 grid((unsigned)((s->max_nctu + NT - 1) / NT), (unsigned)s->n);
-        hevce_commit_kernel<<<grid, NT, sizeof(CommitShared), s->stream>>>(s->d_jobs);
+        const dim3 grid((unsigned)((s->max_nctu + NTC - 1) / NTC), (unsigned)s->n);
+        hevce_commit_kernel<<<grid, NTC, sizeof(CommitShared), s->stream>>>(s->d_jobs, g_dev[s->device].d_tables);
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(s->ev2, s->stream));
@@ -388,22 +440,27 @@ extern "C" int hevce_session_download(hevce_session* s, unsigned char* const* pb
     }
     int rc = stage_reserve(s, s->rcon_total + bytes);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(s->h_stage, s->d_rcon, s->rcon_total, cudaMemcpyDeviceToHost, s->stream));
-    size_t off = s->rcon_total;
-    for (int i = 0; i < s->n; i++) {
-        const size_t len = (size_t)s->results[2 * i];
-        if (len) CK(cudaMemcpyAsync(s->h_stage + off, s->d_out + s->out_off[i], len, cudaMemcpyDeviceToHost, s->stream));
-        off += (len + 15) & ~(size_t)15;
-    }
-    CK(cudaStreamSynchronize(s->stream));
-    off = s->rcon_total;
+    // gather the streams on the device (hevce_pack_kernel), then one copy per direction: reconstructions, streams
+    std::vector<unsigned long long> poff((size_t)s->n);
     std::vector<size_t> soff((size_t)s->n);
+    size_t off = 0;
     for (int i = 0; i < s->n; i++) {
         if (!pbuffers[i] || !img_rcons[i]) return HEVCE_ERR_ARG;
-        soff[i] = off;
+        poff[i] = off;
+        soff[i] = s->rcon_total + off;
         off += ((size_t)s->results[2 * i] + 15) & ~(size_t)15;
         if (stream_len) stream_len[i] = s->results[2 * i];
     }
+    if ((rc = grow(&s->d_pack, &s->c_pack, bytes + 16))) return rc;
+    if ((rc = grow(&s->d_packoff, &s->c_packoff, (size_t)s->n))) return rc;
+    CK(cudaMemcpyAsync(s->d_packoff, poff.data(), (size_t)s->n * sizeof(unsigned long long), cudaMemcpyHostToDevice, s->stream));
+    hevce_pack_kernel<<<s->n, 256, 0, s->stream>>>(s->d_jobs, s->d_packoff, s->d_results, s->d_pack);
+    CK(cudaGetLastError());
+    s->launches += 1;
+    CK(cudaMemcpyAsync(s->h_stage, s->d_rcon, s->rcon_total, cudaMemcpyDeviceToHost, s->stream));
+    if (bytes) CK(cudaMemcpyAsync(s->h_stage + s->rcon_total, s->d_pack, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    off += s->rcon_total;
     parallel_pictures(s->n, off, [&](int i) {
         const Job& j = s->jobs[i];
         memcpy(img_rcons[i], s->h_stage + s->rcon_off[i], (size_t)j.H * j.W);
@@ -463,6 +520,17 @@ extern "C" float hevce_session_kernel_ms(const hevce_session* s) { return s ? s-
 extern "C" float hevce_session_commit_ms(const hevce_session* s) { return s ? s->commit_ms : 0.f; }
 extern "C" int hevce_session_launches(const hevce_session* s) { return s ? s->launches : 0; }
 extern "C" int hevce_session_grid(const hevce_session* s) { return s ? s->grid : 0; }
+extern "C" const char* hevce_session_variant(const hevce_session* s) { return s ? g_variants[s->variant].name : ""; }
+
+// Kernel variant used for the batches configured from now on: "g7", "g4", "g2", "w1", or NULL / "" / "auto" to choose
+// per batch.  returns 0, or HEVCE_ERR_ARG for an unknown name.
+extern "C" int hevce_set_variant(const char* name) {
+    variants_init();
+    if (!name || !*name || !strcmp(name, "auto")) { g_forced_variant = -1; return 0; }
+    for (int v = 0; v < NVARIANT; v++)
+        if (!strcmp(name, g_variants[v].name)) { g_forced_variant = v; return 0; }
+    return HEVCE_ERR_ARG;
+}
 extern "C" long long hevce_session_h2d_bytes(const hevce_session* s) { return s ? s->h2d : 0; }
 extern "C" long long hevce_session_d2h_bytes(const hevce_session* s) { return s ? s->d2h : 0; }
 
@@ -476,7 +544,7 @@ extern "C" void hevce_session_destroy(hevce_session* s) {
     cudaSetDevice(s->device);
     cudaFree(s->d_img); cudaFree(s->d_rcon); cudaFree(s->d_out); cudaFree(s->d_jobs); cudaFree(s->d_order);
     cudaFree(s->d_results); cudaFree(s->d_counter); cudaFree(s->d_slots); cudaFree(s->d_glev); cudaFree(s->d_grec);
-    cudaFree(s->d_lev); cudaFree(s->d_line); cudaFree(s->d_recs); cudaFree(s->d_sse);
+    cudaFree(s->d_lev); cudaFree(s->d_line); cudaFree(s->d_recs); cudaFree(s->d_sse); cudaFree(s->d_pack); cudaFree(s->d_packoff);
     if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -485,11 +553,11 @@ extern "C" void hevce_session_destroy(hevce_session* s) {
     delete s;
 }
 
-#if defined(HEVCE_PROFILE)
+#if defined(HEVCE_PROFILE_DUMP)
 extern "C" __attribute__((visibility("default"))) void hevce_profile_dump(void) {
     unsigned long long c[128], n[128];
-    cudaMemcpyFromSymbol(c, g_phase_cycles, sizeof c);
-    cudaMemcpyFromSymbol(n, g_phase_count, sizeof n);
+    g_variants[g_last_variant].profile(c, n);
+    printf("variant %s\n", g_variants[g_last_variant].name);
     static const char* names[] = {"border", "A", "B", "C", "D+pu/trial", "pu_argmin", "trial(S>8)", "decide", "adopt", "enter", "load", "commit", "misc", "teamA/round", "teamB pixel", "teamB d+cabac", "teamB argmin"};
     unsigned long long tot = 0;
     for (int i = 0; i < P_TA; i++) tot += c[i];   // team tags overlap "D+pu/trial" of the 8x8 nodes

@@ -7,7 +7,11 @@ extern "C" {
 #endif
 int hevce_internal_max_dim(void);
 int hevce_internal_device_count(void);
-int hevce_session_configure(hevce_session *s, int n, const int *ysz, const int *xsz, const int *qpd6);
+int hevce_internal_get_device(void);          /* the calling thread's current CUDA device, -1 if none */
+void hevce_internal_set_device(int device);   /* no-op for device < 0 */
+void hevce_internal_set_copy_threads(int n);  /* host threads used for staging copies by each session */
+hevce_session *hevce_session_create_empty(int device);
+int hevce_session_configure(hevce_session *s, int n, const int *ysz, const int *xsz, const int *qpd6, int max_dim);
 void hevce_session_padded_size(const hevce_session *s, int i, int *H, int *W);
 #ifdef __cplusplus
 }

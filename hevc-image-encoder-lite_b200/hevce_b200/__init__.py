@@ -25,6 +25,7 @@ EXPORTS = [
     "hevce_session_download", "hevce_session_kernel_ms", "hevce_session_commit_ms", "hevce_session_launches", "hevce_session_grid",
     "hevce_session_h2d_bytes", "hevce_session_d2h_bytes", "hevce_session_destroy",
     "hevce_session_quality", "hevce_session_quality_ms", "hevce_session_partition",
+    "hevce_set_variant", "hevce_session_variant", "hevce_get_max_dim", "hevce_release",
 ]
 
 
@@ -53,7 +54,15 @@ def lib():
         L.hevce_set_devices.argtypes = [ctypes.c_int, _ip]
         L.hevce_set_max_dim.restype = ctypes.c_int
         L.hevce_set_max_dim.argtypes = [ctypes.c_int]
+        L.hevce_get_max_dim.restype = ctypes.c_int
+        L.hevce_get_max_dim.argtypes = []
+        L.hevce_release.restype = None
+        L.hevce_release.argtypes = []
         L.hevce_version.restype = ctypes.c_char_p
+        L.hevce_set_variant.restype = ctypes.c_int
+        L.hevce_set_variant.argtypes = [ctypes.c_char_p]
+        L.hevce_session_variant.restype = ctypes.c_char_p
+        L.hevce_session_variant.argtypes = [ctypes.c_void_p]
         L.hevce_measure_int_peak.restype = ctypes.c_double
         L.hevce_measure_int_peak.argtypes = [ctypes.c_int]
         L.hevce_session_create.restype = ctypes.c_void_p
@@ -84,8 +93,9 @@ def lib():
     return _lib
 
 
-def padded(n, limit=8192):
-    return (min(int(n), limit) + 31) // 32 * 32
+def padded(n, limit=None):
+    """Size after the clamp to the library's limit (default 8192, hevce_set_max_dim) and padding to a multiple of 32."""
+    return (min(int(n), limit or get_max_dim()) + 31) // 32 * 32
 
 
 def _ptr_array(arrs):
@@ -98,8 +108,10 @@ def _out_buffers(shapes, limit):
     return outs, rcons
 
 
-def HEVCImageEncoder(img, qpd6, max_dim=8192):
-    """One picture through the drop-in C entry point. Returns (stream bytes, reconstruction HxW uint8)."""
+def HEVCImageEncoder(img, qpd6, max_dim=None):
+    """One picture through the drop-in C entry point. Returns (stream bytes, reconstruction HxW uint8).
+    Output buffers are sized from the library's own size limit (hevce_get_max_dim), not from an argument."""
+    max_dim = get_max_dim()
     img = np.ascontiguousarray(img, dtype=np.uint8)
     if img.ndim != 2:
         raise HevceError(ERR_ARG, "HEVCImageEncoder needs a 2-D uint8 array")
@@ -113,19 +125,24 @@ def HEVCImageEncoder(img, qpd6, max_dim=8192):
     return out[:n].tobytes(), rcon
 
 
-def alloc_outputs(shapes, max_dim=8192):
+def alloc_outputs(shapes, max_dim=None):
     """Caller-owned output buffers (stream, reconstruction) for pictures of the given shapes; reusable across calls,
     exactly like the pbuffer / img_rcon arrays a C caller keeps."""
-    return _out_buffers(shapes, max_dim)
+    return _out_buffers(shapes, get_max_dim())
 
 
-def HEVCImageEncoderBatch(imgs, qpd6, max_dim=8192, outputs=None, copy_streams=True):
+def HEVCImageEncoderBatch(imgs, qpd6, max_dim=None, outputs=None, copy_streams=True):
     """n pictures in one call (sharded over the selected GPUs). qpd6: int or sequence. Returns (streams, recons).
     outputs: buffers from alloc_outputs() to reuse; copy_streams=False returns views into them instead of bytes."""
     imgs = [np.ascontiguousarray(i, dtype=np.uint8) for i in imgs]
     n = len(imgs)
     qs = [int(qpd6)] * n if np.isscalar(qpd6) else [int(q) for q in qpd6]
-    outs, rcons = outputs if outputs is not None else _out_buffers([i.shape for i in imgs], max_dim)
+    limit = get_max_dim()
+    outs, rcons = outputs if outputs is not None else _out_buffers([i.shape for i in imgs], limit)
+    for i, o, r in zip(imgs, outs, rcons):      # the library clamps with ITS limit: never hand it a smaller buffer
+        need = padded(i.shape[0], limit) * padded(i.shape[1], limit)
+        if r.size < need or o.size < 256 + 2 * need:
+            raise HevceError(ERR_ARG, "HEVCImageEncoderBatch: output buffers smaller than the library's size limit requires")
     ys = (ctypes.c_int * n)(*[i.shape[0] for i in imgs])
     xs = (ctypes.c_int * n)(*[i.shape[1] for i in imgs])
     qa = (ctypes.c_int * n)(*qs)
@@ -145,8 +162,24 @@ def set_devices(ordinals):
         raise HevceError(rc, "hevce_set_devices")
 
 
+def set_variant(name=None):
+    """Kernel variant for the following batches: "g7", "g4", "g2", "w1", or None / "auto" to choose per batch."""
+    rc = lib().hevce_set_variant(name.encode() if name else None)
+    if rc < 0:
+        raise HevceError(rc, "hevce_set_variant")
+
+
 def set_max_dim(v):
     return lib().hevce_set_max_dim(int(v))
+
+
+def get_max_dim():
+    return lib().hevce_get_max_dim()
+
+
+def release():
+    """Free the library's cached sessions (HBM buffers and pinned staging of earlier calls)."""
+    lib().hevce_release()
 
 
 def measure_int_peak(device=0):
@@ -159,9 +192,9 @@ def measure_int_peak(device=0):
 class Session:
     """Device-resident batch on one GPU: upload once, encode (timed with CUDA events), download."""
 
-    def __init__(self, device, shapes, qpd6, max_dim=8192):
+    def __init__(self, device, shapes, qpd6, max_dim=None):
         n = len(shapes)
-        self.n, self.shapes, self.max_dim = n, list(shapes), max_dim
+        self.n, self.shapes, self.max_dim = n, list(shapes), get_max_dim()
         qs = [int(qpd6)] * n if np.isscalar(qpd6) else [int(q) for q in qpd6]
         ys = (ctypes.c_int * n)(*[s[0] for s in shapes])
         xs = (ctypes.c_int * n)(*[s[1] for s in shapes])
@@ -224,6 +257,10 @@ class Session:
     @property
     def grid(self):
         return lib().hevce_session_grid(self._h)
+
+    @property
+    def variant(self):
+        return lib().hevce_session_variant(self._h).decode()
 
     @property
     def h2d_bytes(self):

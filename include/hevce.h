@@ -37,7 +37,8 @@ extern "C" {
  *              1643-1644)
  *   qpd6     : 0..4 (QP = 6*qpd6 + 4)
  * returns the stream length in bytes (HEVCe.c:1646), or a negative HEVCE_ERR_* (the reference cannot fail; a
- * negative return is a compatible extension).  Re-entrant and thread-safe like the reference.
+ * negative return is a compatible extension).  Re-entrant and thread-safe like the reference: concurrent callers each
+ * get their own device session (up to four are cached per device), and the caller's current CUDA device is restored.
  */
 HEVCE_API int HEVCImageEncoder(unsigned char *pbuffer, const unsigned char *img, unsigned char *img_rcon,
                      int *ysz, int *xsz, const int qpd6);
@@ -61,6 +62,18 @@ HEVCE_API int hevce_set_devices(int count, const int *ordinals);
 /* Size limit applied by the clamp (default 8192 = the reference's MAX_YSZ / MAX_XSZ, HEVCe.c:62-63).  Values up to
  * 16384 reproduce a reference build whose two limits were raised; returns the previous value. */
 HEVCE_API int hevce_set_max_dim(int max_dim);
+HEVCE_API int hevce_get_max_dim(void);   /* the limit in force; a call captures it once on entry (size output buffers from it) */
+
+/* Free the sessions the library caches between calls (HBM buffers, pinned staging).  Sessions a running call is
+ * using stay.  The reference allocates nothing, so it has no counterpart. */
+HEVCE_API void hevce_release(void);
+
+/* Kernel variant for the batches configured from now on.  The decision kernel is linked in four variants of the same
+ * source: "g7" / "g4" / "g2" = 7 / 4 / 2 same-size pictures per CTA in lock-step (throughput), "w1" = one picture per
+ * CTA with all its threads and nearly all shared memory of the SM (latency: few or large pictures).  NULL, "" or
+ * "auto" (default; also the environment variable HEVCE_VARIANT) chooses per batch.  Every variant produces the same
+ * bytes.  returns 0, or HEVCE_ERR_ARG for an unknown name. */
+HEVCE_API int hevce_set_variant(const char *name);
 
 /* Device-resident session: buffers for a fixed list of pictures on ONE device.  Lets a caller keep inputs in HBM
  * and time the encode kernel alone (bench.py `value`), or overlap its own copies. */
@@ -74,6 +87,7 @@ HEVCE_API float hevce_session_kernel_ms(const hevce_session *s);   /* CUDA-event
 HEVCE_API float hevce_session_commit_ms(const hevce_session *s);   /* ... of the hevce_commit_kernel launch that follows it */
 HEVCE_API int  hevce_session_launches(const hevce_session *s);     /* kernel launches issued so far by this session */
 HEVCE_API int  hevce_session_grid(const hevce_session *s);         /* CTAs of the persistent encode grid */
+HEVCE_API const char *hevce_session_variant(const hevce_session *s); /* kernel variant chosen for the configured batch */
 /* Per-picture quality of the last encode, reduced on the device: mean squared error and PSNR between source and
  * reconstruction over the area both cover, MSE floored at 1e-9 (calcImagePSNR, HEVCeMain.c:116-133, printed by the
  * reference CLI at HEVCeMain.c:201-212).  mse / psnr: n doubles each, either may be NULL.  HEVCE_ERR_STATE before the

@@ -8,14 +8,14 @@
 
 #include "hevce_core.h"
 
-namespace hevce { int g_sim_order = 0; Shared* g_sim_sm = nullptr; Tables* g_sim_tb = nullptr; CommitShared* g_sim_csm = nullptr; }
+namespace HEVCE_NS { int g_sim_order = 0; Shared* g_sim_sm = nullptr; Tables* g_sim_tb = nullptr; CommitShared* g_sim_csm = nullptr; }
 
-static std::vector<hevce::CtuRec> g_last_recs;
+static std::vector<HEVCE_NS::CtuRec> g_last_recs;
 static int g_last_h = 0, g_last_w = 0;
 
 extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned char* img, unsigned char* rcon,
                                 int* ysz, int* xsz, int q, int order, int max_dim, int* err) {
-    using namespace hevce;
+    using namespace HEVCE_NS;
     g_sim_order = order;
     static Tables tables;
     fill_tables(tables);
@@ -37,14 +37,14 @@ extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned 
     memset(sm, 0xA5, sizeof(Shared));   // shared memory is not zeroed on the GPU either
     g_sim_sm = sm;
     g_sim_tb = &tables;
-    encode_picture(job, tables, *sm, sc);
+    encode_picture(job, *sm, sc);
     delete sm;
     // commit pass (hevce_commit_kernel on the GPU): one CTU at a time here
     CommitShared* cs = new CommitShared;
     memset(cs, 0x5A, sizeof(CommitShared));
     cs->tb = tables;
     g_sim_csm = cs;
-    for (int c = 0; c < nctu; c++) commit_ctu(job, order == 1 ? nctu - 1 - c : c, (c * 7) % NT);
+    for (int c = 0; c < nctu; c++) commit_ctu(job, order == 1 ? nctu - 1 - c : c, (c * 7) % NTC);
     delete cs;
     *ysz = job.H; *xsz = job.W;
     g_last_recs = recs; g_last_h = job.H; g_last_w = job.W;
@@ -54,7 +54,7 @@ extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned 
 
 // decisions of the last hevce_sim_encode call: (H/4)x(W/4) CU sizes and modes, (H/8)x(W/8) CU kinds
 extern "C" void hevce_sim_last_partition(unsigned char* cu_size, unsigned char* mode, unsigned char* kind) {
-    hevce::unpack_partition(g_last_recs.data(), g_last_h, g_last_w, cu_size, mode, kind);
+    HEVCE_NS::unpack_partition(g_last_recs.data(), g_last_h, g_last_w, cu_size, mode, kind);
 }
 
-extern "C" int hevce_sim_shared_bytes() { return (int)sizeof(hevce::Shared); }
+extern "C" int hevce_sim_shared_bytes() { return (int)sizeof(HEVCE_NS::Shared); }

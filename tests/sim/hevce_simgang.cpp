@@ -13,21 +13,22 @@
 
 #include "hevce_core.h"
 
-namespace hevce {
+namespace HEVCE_NS {
 int g_sim_order = 0;
+int g_sim_nlive = 1;
 Shared* g_sim_sms = nullptr;
 Tables* g_sim_tb = nullptr;
 CommitShared* g_sim_csm = nullptr;
 thread_local int g_sim_member = 0;
 static pthread_barrier_t g_bar[3];
 void sim_barrier(int id) { pthread_barrier_wait(&g_bar[id]); }
-}   // namespace hevce
+}   // namespace HEVCE_NS
 
-// Encode `n` (1..GANG) pictures of identical size h x w as ONE gang (a short gang repeats its first picture, as the
-// kernel does).  outs[i] / rcons[i]: per-picture buffers (cap bytes / padded size); lens[i], errs[i] are written.
+// Encode `n` (1..GANG) pictures of identical size h x w as ONE gang (the slots of a short gang stay empty: only the live
+// pictures take part in the barriers, as in the kernel).  outs[i] / rcons[i]: per-picture buffers (cap bytes / padded size); lens[i], errs[i] are written.
 extern "C" int hevce_simgang_encode(int n, unsigned char* const* outs, int out_cap, const unsigned char* const* imgs,
                                     unsigned char* const* rcons, int h, int w, const int* qs, int order, int* lens, int* errs) {
-    using namespace hevce;
+    using namespace HEVCE_NS;
     if (n < 1 || n > GANG) return -1;
     g_sim_order = order;
     static Tables tables;
@@ -37,18 +38,13 @@ extern "C" int hevce_simgang_encode(int n, unsigned char* const* outs, int out_c
     std::vector<Job> jobs(GANG);
     std::vector<std::vector<s16>> glev(GANG), lev(GANG);
     std::vector<std::vector<CtuRec>> recs(GANG);
-    std::vector<std::vector<u8>> grec(GANG), line(GANG), dup_out(GANG), dup_rcon(GANG);
+    std::vector<std::vector<u8>> grec(GANG), line(GANG);
     std::vector<Scratch> sc(GANG);
     std::vector<int> result(2 * GANG, 0);
-    for (int m = 0; m < GANG; m++) {
-        const int src = m < n ? m : 0;
+    for (int m = 0; m < n; m++) {
         Job& j = jobs[m];
-        j.img = imgs[src]; j.src_h = h; j.src_w = w; j.H = H; j.W = W; j.q = qs[src]; j.out_cap = out_cap;
-        if (m < n) { j.out = outs[m]; j.rcon = rcons[m]; }
-        else {   // the duplicate works on private buffers here (on the GPU it rewrites the first picture's bytes)
-            dup_out[m].resize(out_cap); dup_rcon[m].resize((size_t)H * W);
-            j.out = dup_out[m].data(); j.rcon = dup_rcon[m].data();
-        }
+        j.img = imgs[m]; j.src_h = h; j.src_w = w; j.H = H; j.W = W; j.q = qs[m]; j.out_cap = out_cap;
+        j.out = outs[m]; j.rcon = rcons[m];
         j.result = &result[2 * m];
         glev[m].resize((size_t)NCAND * LEV_STRIDE + 16); lev[m].resize((size_t)nctu * CTU * CTU); recs[m].resize(nctu);
         grec[m].resize((size_t)NREC * CTU * CTU); line[m].resize(W / 4 + 8);
@@ -58,12 +54,13 @@ extern "C" int hevce_simgang_encode(int n, unsigned char* const* outs, int out_c
     Shared* sms = (Shared*)aligned_alloc(16, sizeof(Shared) * GANG);
     memset(sms, 0xA5, sizeof(Shared) * GANG);
     g_sim_sms = sms;
-    for (int b = 0; b < 3; b++) pthread_barrier_init(&g_bar[b], nullptr, GANG);
+    g_sim_nlive = n;
+    for (int b = 0; b < 3; b++) pthread_barrier_init(&g_bar[b], nullptr, n);
     std::vector<std::thread> th;
-    for (int m = 0; m < GANG; m++)
+    for (int m = 0; m < n; m++)
         th.emplace_back([&, m] {
             g_sim_member = m;
-            encode_picture(jobs[m], tables, sms[m], sc[m]);
+            encode_picture(jobs[m], sms[m], sc[m]);
         });
     for (auto& t : th) t.join();
     for (int b = 0; b < 3; b++) pthread_barrier_destroy(&g_bar[b]);
@@ -73,7 +70,7 @@ extern "C" int hevce_simgang_encode(int n, unsigned char* const* outs, int out_c
     cs->tb = tables;
     g_sim_csm = cs;
     for (int m = 0; m < n; m++) {
-        for (int c = 0; c < nctu; c++) commit_ctu(jobs[m], c, (c * 5 + m) % NT);
+        for (int c = 0; c < nctu; c++) commit_ctu(jobs[m], c, (c * 5 + m) % NTC);
         lens[m] = result[2 * m];
         errs[m] = result[2 * m + 1];
     }
@@ -81,4 +78,4 @@ extern "C" int hevce_simgang_encode(int n, unsigned char* const* outs, int out_c
     return 0;
 }
 
-extern "C" int hevce_simgang_size() { return hevce::GANG; }
+extern "C" int hevce_simgang_size() { return HEVCE_NS::GANG; }

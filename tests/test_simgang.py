@@ -30,7 +30,7 @@ def test_full_gang_mixed_qpd6():
 
 
 def test_short_gang_and_padding():
-    imgs = crops(3, 45, 70)                      # padded to 64x96; the gang repeats its first picture to fill up
+    imgs = crops(3, 45, 70)                      # padded to 64x96; four of the seven slots stay empty
     for i, (s, r, err) in enumerate(S.simgang_encode(imgs, [2, 4, 0])):
         so, ro = R.oracle_encode(imgs[i], [2, 4, 0][i])
         assert err == 0 and s == so and np.array_equal(r, ro), i
@@ -82,3 +82,24 @@ int main() {
     assert out.returncode == 0 and "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
     rows = [l.split() for l in out.stdout.strip().splitlines()]
     assert len(rows) == S.simgang().hevce_simgang_size() and all(int(r[1]) > 100 and int(r[2]) == 0 for r in rows)
+
+
+@pytest.mark.parametrize("variant", ["g4", "g2", "w1"])
+def test_other_variants_full_and_short_gangs(variant):
+    """The 4- and 2-picture gangs and the wide one-picture variant (other thread counts per picture, other team sizes,
+    few trial lanes per warp, the large pool plan of the wide variant) through the same source, incl. a short gang."""
+    g = S.simgang(variant).hevce_simgang_size()
+    for n in sorted({g, max(1, g - 1)}):
+        imgs, qs = crops(n, 45, 70), [(2 * i + 1) % 5 for i in range(n)]
+        for i, (s, r, err) in enumerate(S.simgang_encode(imgs, qs, 0, variant=variant)):
+            so, ro = R.oracle_encode(imgs[i], qs[i])
+            assert err == 0 and s == so and np.array_equal(r, ro), (variant, n, i)
+
+
+def test_wide_variant_single_thread_simulator_permuted():
+    """The wide pool plan (all 35 candidates of a 16x16 / 32x32 step in one round) under permuted work-item orders."""
+    img = WL.config3_image(7)[100:164, 300:396].copy()
+    for q, order in ((0, 1), (2, 3), (4, 5)):
+        s, r, err = S.sim_encode(img, q, order, variant="w1")
+        so, ro = R.oracle_encode(img, q)
+        assert err == 0 and s == so and np.array_equal(r, ro), (q, order)

@@ -34,11 +34,11 @@ def config3_batch(first, count):
     return [config3_image(i, K) for i in range(first, first + count)]
 
 
-def config4_image(i, K=None, h=2160, w=3840):
+def config4_image(i, K=None, h=2160, w=3840, seed=4000):
     """Image i of config 4: 5x5 mosaic of Kodak tiles (tile choice integers(1,25), per-tile h/v flips from
     default_rng(4000+i)), cropped to h x w."""
     K = K or kodak_landscape()
-    rng = np.random.default_rng(4000 + i)
+    rng = np.random.default_rng(seed + i)
     ty, tx = -(-h // KODAK_H), -(-w // KODAK_W)
     rows = []
     for _ in range(ty):
@@ -52,6 +52,16 @@ def config4_image(i, K=None, h=2160, w=3840):
             row.append(t)
         rows.append(np.concatenate(row, axis=1))
     return np.ascontiguousarray(np.concatenate(rows, axis=0)[:h, :w])
+
+
+CONFIG5_H, CONFIG5_W = 11993, 15991
+
+
+def config5_image(K=None, h=CONFIG5_H, w=CONFIG5_W):
+    """The picture of config 5: the config-4 construction as a 21x24 mosaic from default_rng(5000),
+    cropped to 15991x11993 (w x h), which the encoder pads to 16000x12000 (raised limit) or crops to the top-left
+    8192x8192 (drop-in limit, HEVCe.c:1581-1582)."""
+    return config4_image(0, K, h=h, w=w, seed=5000)
 
 
 def shard_range(n, rank, world):

@@ -11,7 +11,8 @@ import hevce_b200 as H  # noqa: E402
 import workloads as WL  # noqa: E402
 
 n, h, w, q, reps = (int(v) for v in (sys.argv[1:] + ["148", "64", "64", "2", "2"][len(sys.argv) - 1:]))
-imgs = [WL.config3_image(i)[100:100 + h, 200:200 + w].copy() for i in range(n)]
+oy, ox = min(100, 512 - h), min(200, 768 - w)   # full-size pictures: the bench workload itself
+imgs = [WL.config3_image(i)[oy:oy + h, ox:ox + w].copy() for i in range(n)]
 ses = H.Session(0, [i.shape for i in imgs], q)
 ses.upload(imgs)
 for r in range(reps):
