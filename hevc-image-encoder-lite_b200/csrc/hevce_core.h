@@ -64,6 +64,15 @@
 #ifndef HEVCE_OPT_WIDE
 #define HEVCE_OPT_WIDE 0
 #endif
+#ifndef HEVCE_OPT_TRACKS   // 1: parent || child -- a picture's threads split into three tracks: the 8x8 chain, the 16x16
+#define HEVCE_OPT_TRACKS 0 //    nodes' own candidates, the 32x32 node's own candidates (HEVCE_OPT_TRK_C threads + 2 equal halves of the rest)
+#endif
+#ifndef HEVCE_OPT_TRK_C
+#define HEVCE_OPT_TRK_C HEVCE_OPT_NT
+#endif
+#ifndef HEVCE_OPT_LPW_P    // trial lanes per warp on the two parent tracks
+#define HEVCE_OPT_LPW_P HEVCE_OPT_LPW
+#endif
 #ifndef HEVCE_NS
 #define HEVCE_NS hevce
 #endif
@@ -82,8 +91,22 @@ constexpr int NT = HEVCE_OPT_NT;   // threads per picture (a multiple of 64)
 constexpr int GANG = HEVCE_OPT_GANG;            // pictures per CTA (lock-step groups of NT threads)
 constexpr int LPW = HEVCE_OPT_LPW;
 constexpr bool WIDE = HEVCE_OPT_WIDE != 0;
-constexpr int NTA = (NT / 2) / 32 * 32, NTB = NT - NTA;   // the two thread teams of a picture on 8x8 nodes: [0, NTA) and [NTA, NT)
-static_assert(NT % 32 == 0 && NTA >= 32 && LPW >= 1 && LPW <= 32, "bad kernel variant");
+// Tracks (parent || child, SURVEY.md section 7.3-1: a node's own candidates depend only on its entry snapshot and on
+// samples outside the CU, so they can be evaluated while its children run; only the final ">=" waits): track 0 = the
+// 8x8 nodes plus every decision / adoption, track 1 = the candidates of the 16x16 nodes, track 2 = those of the 32x32 node.
+constexpr bool TRACKS = HEVCE_OPT_TRACKS != 0;
+constexpr int NTRACK = TRACKS ? 3 : 1;
+constexpr int TRK_C = TRACKS ? HEVCE_OPT_TRK_C : NT;      // threads of track 0
+constexpr int TRK_P = TRACKS ? (NT - TRK_C) / 2 : 0;      // threads of track 1 and of track 2
+constexpr int LPW_P = HEVCE_OPT_LPW_P;
+constexpr int NTA = (TRK_C / 2) / 32 * 32, NTB = TRK_C - NTA;   // the two thread teams of track 0 on 8x8 nodes: [0, NTA) and [NTA, TRK_C)
+static_assert(NT % 32 == 0 && NTA >= 32 && LPW >= 1 && LPW <= 32 && LPW_P >= 1 && LPW_P <= 32, "bad kernel variant");
+static_assert(!TRACKS || (GANG == 1 && TRK_C % 64 == 0 && TRK_P % 32 == 0 && TRK_P >= 96 && TRK_C + 2 * TRK_P == NT), "bad track split");
+HEVCE_HD inline int trk_of_tid(int tid) { return (!TRACKS || tid < TRK_C) ? 0 : tid < TRK_C + TRK_P ? 1 : 2; }
+HEVCE_HD inline int trk_t0(int t) { return t == 0 ? 0 : t == 1 ? TRK_C : TRK_C + TRK_P; }
+HEVCE_HD inline int trk_size(int t) { return t == 0 ? TRK_C : TRK_P; }
+HEVCE_HD inline int trk_lpw(int t) { return t == 0 ? LPW : LPW_P; }
+template <int S> struct TrackOf { static constexpr int value = !TRACKS ? 0 : S == 8 ? 0 : S == 16 ? 1 : 2; };
 constexpr int NTC = 128;           // threads per block of the commit kernel (one CTU each)
 constexpr int NLANE = 70;          // trial-coder lanes with a private context set (the 35 NxN-PU lanes reuse 0..34)
 constexpr int NCAND = 105;         // trial-coder lanes of a CU node: 35 one-TU + 35 four-TU + 35 NxN-PU candidates
@@ -457,8 +480,8 @@ struct Scratch {       // per picture slot, global memory (L2-resident working s
     u8* msz_line;      // CU-size map row of the CTU row above, W/4 entries
 };
 
-constexpr int POOL_BYTES = WIDE ? 189440 : 18624;
-constexpr int AUX_CODER = WIDE ? 187456 : 16640;   // pool tail: trial-coder results (free whenever they are used)
+constexpr int POOL_BYTES = TRACKS ? 53248 : WIDE ? 189440 : 18624;
+constexpr int AUX_CODER = POOL_BYTES - 1984;       // pool tail: trial-coder results (free whenever they are used)
 
 struct Shared {
     alignas(16) u8 pool[POOL_BYTES];    // per-node carve-up: work blocks, predictions, borders (see Plan<S>)
@@ -494,60 +517,69 @@ HEVCE_HD inline Coder* cand_coder(Shared& sm) { return (Coder*)(sm.pool + AUX_CO
 // gang leaves slots empty; their threads skip the picture and wait at the CTA barrier of the work queue).
 struct GangCtl { int nlive; int next; };
 
-// The picture's shared-memory block.  Non-inlined functions fetch it through this accessor instead of taking a
-// reference parameter: the compiler then knows the address space and emits LDS/STS instead of generic loads.
-// The constant tables exist once per CTA, behind the GANG picture blocks.
+// Shared-memory blocks.  Every track of every picture slot owns one `Shared` block (index slot * NTRACK + track): its
+// pool, lane contexts, candidate results and scratch pointers are the track's; the picture-level fields (window,
+// original, maps, live / snapshot coder state ...) are those of the picture's track-0 block (pic_sm()).  Non-inlined
+// functions fetch the blocks through these accessors instead of taking reference parameters: the compiler then knows
+// the address space and emits LDS/STS instead of generic loads.  The constant tables exist once per CTA, behind the blocks.
+constexpr int NBLOCK = GANG * NTRACK;
 #if defined(__CUDA_ARCH__)
 extern __shared__ __align__(16) unsigned char hevce_smem[];
-__device__ __forceinline__ Shared& my_sm() { return reinterpret_cast<Shared*>(hevce_smem)[threadIdx.x / NT]; }
-__device__ __forceinline__ Tables& my_tb() { return *reinterpret_cast<Tables*>(hevce_smem + GANG * sizeof(Shared)); }
-__device__ __forceinline__ Shared& gang_sm(int p) { return reinterpret_cast<Shared*>(hevce_smem)[p]; }
-__device__ __forceinline__ GangCtl& gang_ctl() { return *reinterpret_cast<GangCtl*>(hevce_smem + GANG * sizeof(Shared) + sizeof(Tables)); }
+#define HEVCE_SLOT ((int)(threadIdx.x / NT))
+#define HEVCE_PTID ((int)(threadIdx.x % NT))                       /* thread of the picture */
+#define HEVCE_TRK trk_of_tid(HEVCE_PTID)
+#define HEVCE_TID (HEVCE_PTID - trk_t0(HEVCE_TRK))                 /* thread of the track   */
+__device__ __forceinline__ Shared& blk_sm(int b) { return reinterpret_cast<Shared*>(hevce_smem)[b]; }
+__device__ __forceinline__ Tables& my_tb() { return *reinterpret_cast<Tables*>(hevce_smem + NBLOCK * sizeof(Shared)); }
+__device__ __forceinline__ GangCtl& gang_ctl() { return *reinterpret_cast<GangCtl*>(hevce_smem + NBLOCK * sizeof(Shared) + sizeof(Tables)); }
 __device__ __forceinline__ int gang_live() { return GANG == 1 ? 1 : gang_ctl().nlive; }
 #elif defined(__CUDACC__)
-inline Shared& my_sm() { return *static_cast<Shared*>(nullptr); }   // host pass of nvcc: declared, never executed
-inline Shared& gang_sm(int) { return *static_cast<Shared*>(nullptr); }
+#define HEVCE_SLOT 0
+#define HEVCE_PTID 0
+#define HEVCE_TRK 0
+#define HEVCE_TID 0
+inline Shared& blk_sm(int) { return *static_cast<Shared*>(nullptr); }   // host pass of nvcc: declared, never executed
 inline Tables& my_tb() { return *static_cast<Tables*>(nullptr); }
 inline GangCtl& gang_ctl() { return *static_cast<GangCtl*>(nullptr); }
 inline int gang_live() { return GANG; }
-#elif defined(HEVCE_SIM_GANG)
-// gang simulator (tests/sim): one host thread per picture of a gang, real barriers between the phases
-extern Shared* g_sim_sms;                                            // GANG picture blocks
+extern thread_local int g_sim_trk;   // the host pass parses the simulator macros below, it never runs them
+#else
+// simulators (tests/sim): HEVCE_SIM_GANG = one host thread per picture of a gang, HEVCE_SIM_TRACKS = one host thread
+// per track of one picture, neither = one thread; real barriers between the host threads
+extern Shared* g_sim_sms;                                            // NBLOCK blocks
 extern Tables* g_sim_tb;
 extern int g_sim_nlive;                                              // live pictures of the gang
 extern thread_local int g_sim_member;                                // this thread's picture slot
-void sim_barrier(int id);                                            // 0: CTA-wide, 1 / 2: the two teams
-inline Shared& my_sm() { return g_sim_sms[g_sim_member]; }
-inline Shared& gang_sm(int p) { return g_sim_sms[p]; }
+extern thread_local int g_sim_trk;                                   // the track this thread is executing
+void sim_barrier(int id, int parties);
+#define HEVCE_SLOT g_sim_member
+#define HEVCE_TRK g_sim_trk
+inline Shared& blk_sm(int b) { return g_sim_sms[b]; }
 inline Tables& my_tb() { return *g_sim_tb; }
 inline int gang_live() { return g_sim_nlive; }
-#else
-extern Shared* g_sim_sm;                                             // CTA simulator (tests/sim)
-extern Tables* g_sim_tb;
-inline Shared& my_sm() { return *g_sim_sm; }
-inline Shared& gang_sm(int) { return *g_sim_sm; }
-inline Tables& my_tb() { return *g_sim_tb; }
-inline int gang_live() { return 1; }
 #endif
+#define my_sm() blk_sm(HEVCE_SLOT * NTRACK + HEVCE_TRK)                /* the executing track's block       */
+#define pic_sm() blk_sm(HEVCE_SLOT * NTRACK)                          /* the picture-level state           */
+#define gang_sm(p) blk_sm((p) * NTRACK)                               /* picture p of the gang (track 0)   */
 static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail too small");
 
-// ---- thread <-> work mappings (shared by the kernel and the gang simulator) ---------------------------------------
-// Teams: id 0 = all NT threads of a picture, 1 = team A [0, NTA), 2 = team B [NTA, NT).
+// ---- thread <-> work mappings (shared by the kernel and the simulators) --------------------------------------------
+// Teams: id 0 = all threads of the track, 1 = team A [0, NTA), 2 = team B [NTA, TRK_C) (track 0 only).
 HEVCE_HD inline int team_t0(int id) { return id == 2 ? NTA : 0; }
-HEVCE_HD inline int team_size(int id) { return id == 0 ? NT : id == 1 ? NTA : NTB; }
-// first work item of picture thread `tid` in a phase of team `id` whose item 0 sits on team thread `off` (mod team size);
+HEVCE_HD inline int team_size(int id, int trk) { return id == 0 ? trk_size(trk) : id == 1 ? NTA : NTB; }
+// first work item of track thread `tid` in a phase of team `id` whose item 0 sits on team thread `off` (mod team size);
 // n when the thread is not in the team
-HEVCE_HD inline int team_first(int tid, int id, int off, int n) {
+HEVCE_HD inline int team_first(int tid, int trk, int id, int off, int n) {
     const int r = tid - team_t0(id);
-    if (id == 0) return (r + NT - off % NT) % NT;
+    if (id == 0) return trk == 0 ? (r + TRK_C - off % TRK_C) % TRK_C : (r + TRK_P - off % (TRK_P ? TRK_P : 1)) % (TRK_P ? TRK_P : 1);
     if (id == 1) return (unsigned)r < (unsigned)NTA ? (r + NTA - off % NTA) % NTA : n;
     return (unsigned)r < (unsigned)NTB ? (r + NTB - off % NTB) % NTB : n;
 }
-// Trial-coder lanes: thread x of a linear thread space hosts lane (x/32)*LPW + x%32 when x%32 < LPW (LPW = 32: every
-// thread hosts a lane, lanes packed into full warps; small LPW: few lanes per warp, less divergence per warp).
-HEVCE_HD inline int host_lane(int x) { return (x & 31) < LPW ? (x >> 5) * LPW + (x & 31) : -1; }
-HEVCE_HD inline int lane_capacity(int nthreads) { return (nthreads >> 5) * LPW; }
-HEVCE_HD inline int round_lanes(int n) { return (n + LPW - 1) / LPW * LPW; }   // next warp boundary in lane space
+// Trial-coder lanes: thread x of a linear thread space hosts lane (x/32)*lpw + x%32 when x%32 < lpw (lpw = 32: every
+// thread hosts a lane, lanes packed into full warps; small lpw: few lanes per warp, less divergence per warp).
+HEVCE_HD inline int host_lane(int x, int lpw) { return (x & 31) < lpw ? (x >> 5) * lpw + (x & 31) : -1; }
+HEVCE_HD inline int lane_capacity(int nthreads, int lpw) { return (nthreads >> 5) * lpw; }
+HEVCE_HD inline int round_lanes(int n, int lpw) { return (n + lpw - 1) / lpw * lpw; }   // next warp boundary in lane space
 // team-B threads of the live pictures as one linear space: slot * NTB + (tid - NTA); -1 for team-A threads
 HEVCE_HD inline int upper_index(int slot, int tid) { return tid >= NTA ? slot * NTB + tid - NTA : -1; }
 // Items shared by the team-B threads that host none of the first `nlanes` lanes (whole warps); when every warp hosts a
@@ -559,39 +591,46 @@ HEVCE_HD inline int upper_free_first(int ub, int nlanes, int nlive, int n, int& 
     stride = (nw - hostw) * 32;
     return ub >= hostw * 32 ? ub - hostw * 32 : n;
 }
+// barrier ids: 0 work queue (all threads of the CTA), 1 / 2 the teams of track 0, 3 all live threads, 4..6 one track,
+// 7 / 8 rendezvous of track 0 with track 1 / 2
+enum { BAR_TEAM_A = 1, BAR_TEAM_B = 2, BAR_PICTURES = 3, BAR_TRACK0 = 4, BAR_RDV1 = 7, BAR_RDV2 = 8 };
 
-// work-item phases.  On the GPU a phase is a strided loop over the CTA's threads followed by a barrier;
-// in the simulator it is a loop over the items in a permuted order.
+// work-item phases.  On the GPU a phase is a strided loop over the threads of a track (or team) followed by a barrier;
+// in the simulators it is a loop over the items in a permuted order.
 #if defined(__CUDA_ARCH__)
 // A CTA holds up to GANG pictures of identical size, one per group of NT threads; the groups run the same phases in
 // lock-step (barriers over the live pictures), so every warp of the SM executes the same code at the same time.
-#define HEVCE_SLOT ((int)(threadIdx.x / NT))
-#define HEVCE_TID ((int)(threadIdx.x % NT))
-#define PAR_FOR(item, n) for (int item = HEVCE_TID; item < (n); item += NT)
-// threads of team `id` of the picture only; item 0 starts at team thread `off`
-#define PAR_FOR_TEAM(item, n, id, off) for (int item = team_first(HEVCE_TID, (id), (off), (n)); item < (n); item += team_size(id))
-// 8x8 nodes split every picture's threads into two teams that run independent phase chains; a team's barrier spans the
-// same team of all live pictures of the gang (their trial lanes are packed across pictures)
+#define PAR_FOR(item, n) for (int item = HEVCE_TID, st_##item = trk_size(HEVCE_TRK); item < (n); item += st_##item)
+#define PAR_FOR_ALL(item, n) for (int item = HEVCE_PTID; item < (n); item += NT)   /* all threads of the picture */
+// threads of team `id` of the track only; item 0 starts at team thread `off`
+#define PAR_FOR_TEAM(item, n, id, off) for (int item = team_first(HEVCE_TID, HEVCE_TRK, (id), (off), (n)), st_##item = team_size((id), HEVCE_TRK); item < (n); item += st_##item)
+// 8x8 nodes split track 0 into two teams that run independent phase chains; a team's barrier spans the same team of
+// all live pictures of the gang (their trial lanes are packed across pictures)
 #define TEAM_A if (HEVCE_TID < NTA)
 #define TEAM_B else
-#define TEAM_JOIN() ((void)0)   // the CTA-wide barrier that follows is the join
+#define TEAM_JOIN() ((void)0)   // the track-wide barrier that follows is the join
 #define HEVCE_BAR(id, cnt) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(cnt) : "memory")
 #define TEAM_SYNC(id) HEVCE_BAR(id, gang_live() * ((id) == 1 ? NTA : NTB))
-// Trial-coder lanes of all live pictures, hosted by the CTA's threads (GANG_FOR) or by the team-B threads (GANG_FOR_UPPER)
+// Trial-coder lanes of all live pictures, hosted by the track's threads (GANG_FOR) or by the team-B threads (GANG_FOR_UPPER)
 #define GANG_RT (gang_live())
-#define GANG_FOR(L, n) for (int L = host_lane((int)threadIdx.x), cap_ = lane_capacity(gang_live() * NT); (unsigned)L < (unsigned)(n); L += cap_)
-#define GANG_FOR_UPPER(u, n) for (int u = HEVCE_TID >= NTA ? host_lane(upper_index(HEVCE_SLOT, HEVCE_TID)) : -1, cap_ = lane_capacity(gang_live() * NTB); (unsigned)u < (unsigned)(n); u += cap_)
+#define GANG_FOR(L, n) for (int L = host_lane(HEVCE_SLOT * trk_size(HEVCE_TRK) + HEVCE_TID, trk_lpw(HEVCE_TRK)), cap_ = lane_capacity(gang_live() * trk_size(HEVCE_TRK), trk_lpw(HEVCE_TRK)); (unsigned)L < (unsigned)(n); L += cap_)
+#define GANG_FOR_UPPER(u, n) for (int u = HEVCE_TID >= NTA ? host_lane(upper_index(HEVCE_SLOT, HEVCE_TID), LPW) : -1, cap_ = lane_capacity(gang_live() * NTB, LPW); (unsigned)u < (unsigned)(n); u += cap_)
 // the team-B threads that host none of the `first` lanes share n items of any picture of the gang
 #define GANG_FOR_UPPER_FREE(it, first, n) for (int st_ = 1, it = upper_free_first(upper_index(HEVCE_SLOT, HEVCE_TID), (first), gang_live(), (n), st_); it < (n); it += st_)
-#define PHASE_END() HEVCE_BAR(3, gang_live() * NT)
+// end of a phase: the threads of this track (of all live pictures); without tracks that is every live thread
+#define PHASE_END() do { if (TRACKS) HEVCE_BAR(BAR_TRACK0 + HEVCE_TRK, gang_live() * trk_size(HEVCE_TRK)); else HEVCE_BAR(BAR_PICTURES, gang_live() * NT); } while (0)
+#define BAR_ALL() HEVCE_BAR(BAR_PICTURES, gang_live() * NT)
+// rendezvous of track 0 with parent track t (a no-op for the third track)
+#define TRACK_RDV(t) do { if (HEVCE_TRK == 0 || HEVCE_TRK == (t)) HEVCE_BAR(BAR_RDV1 - 1 + (t), gang_live() * (TRK_C + TRK_P)); } while (0)
+#define ON_TRACK(t) if (HEVCE_TRK == (t))
 // between the pixel phases A..D of one round: all lines of a candidate's TU are work items of the same warp (T <= 32
 // consecutive items, groups start at multiples of T), so the hand-over needs no CTA- or team-wide barrier
 #define WARP_SYNC() __syncwarp()
 #if defined(HEVCE_PROFILE)   // per-phase latency histogram (development builds only)
 extern __device__ unsigned long long g_phase_cycles[128];
 extern __device__ unsigned long long g_phase_count[128];
-#define PHASE_END_T(tag) do { PHASE_END(); if (threadIdx.x == 0) { const long long t_ = clock64(); \
-    atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - sm.prof_last)); atomicAdd(&g_phase_count[tag], 1ull); sm.prof_last = t_; } } while (0)
+#define PHASE_END_T(tag) do { PHASE_END(); if (threadIdx.x == 0) { Shared& pm_ = pic_sm(); const long long t_ = clock64(); \
+    atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - pm_.prof_last)); atomicAdd(&g_phase_count[tag], 1ull); pm_.prof_last = t_; } } while (0)
 #define TEAM_PROF_BEGIN() long long tp_ = clock64()
 #define TEAM_PROF(tag, lead) do { if (threadIdx.x == (lead)) { const long long t_ = clock64(); \
     atomicAdd(&g_phase_cycles[tag], (unsigned long long)(t_ - tp_)); atomicAdd(&g_phase_count[tag], 1ull); tp_ = t_; } } while (0)
@@ -613,47 +652,68 @@ inline int sim_item(int i, int n) {
     return (int)(((long long)i * a + 7) % n);
 }
 #define PAR_FOR(item, n) for (int item##_i = 0, item = 0; item##_i < (n) && ((item = sim_item(item##_i, (n))), true); item##_i++)
+#define PAR_FOR_ALL(item, n) PAR_FOR(item, n)
 #define PAR_FOR_TEAM(item, n, id, off) PAR_FOR(item, n)
-#if defined(HEVCE_SIM_GANG)
-// the two teams of a picture really run side by side: team A on a helper thread, team B on the picture's thread
-#define TEAM_A auto team_a_ = [&](int member_) { g_sim_member = member_;
-#define TEAM_B }; std::thread team_a_thread_(team_a_, g_sim_member);
-#define TEAM_JOIN() team_a_thread_.join()
-#else
-#define TEAM_A
-#define TEAM_B
-#define TEAM_JOIN() ((void)0)
-#endif
 #define WARP_SYNC() ((void)0)
 #define TEAM_PROF_BEGIN() ((void)0)
 #define TEAM_PROF(tag, lead) ((void)0)
+#define PHASE_END_T(tag) PHASE_END()
+#if defined(HEVCE_SIM_TRACKS)
+// One host thread per track of ONE picture: a thread executes only its own track's sections, the rendezvous and the
+// picture-wide barriers are real.  Inside a track the phases run sequentially (teams one after the other).
+extern thread_local int g_sim_my_track;                              // the track this host thread stands for
+#define ON_TRACK(t) if (g_sim_my_track == (t) && ((g_sim_trk = (t)), true))
+#define TRACK_RDV(t) do { if (g_sim_my_track == 0 || g_sim_my_track == (t)) sim_barrier(BAR_RDV1 - 1 + (t), 2); } while (0)
+#define BAR_ALL() sim_barrier(BAR_PICTURES, NTRACK)
+#define PAR_FOR_ALL_OWNER (g_sim_my_track == 0)                       /* picture-wide loops: run once, by track 0's thread */
+#else
+// tracks one after the other on the calling thread: a parent's candidates right after its snapshot, then the children
+#define ON_TRACK(t) if ((g_sim_trk = (t)), true)
+#define TRACK_RDV(t) ((void)(g_sim_trk = 0))
+#define PAR_FOR_ALL_OWNER true
+#endif
 #if defined(HEVCE_SIM_GANG)
+// the two teams of a picture really run side by side: team A on a helper thread, team B on the picture's thread
+#define TEAM_A auto team_a_ = [&](int member_) { g_sim_member = member_; g_sim_trk = 0;
+#define TEAM_B }; std::thread team_a_thread_(team_a_, g_sim_member);
+#define TEAM_JOIN() team_a_thread_.join()
 // Host thread m stands for the NT threads of picture slot m: it runs the gang-wide loops for exactly the lane / thread
 // indices those threads own on the GPU (same mapping functions), so the cross-picture packing and the barrier structure
 // are exercised for real (each thread runs its team A section, then its team B section; the team barriers span the threads).
 #define GANG_RT (gang_live())
-#define GANG_FOR(L, n) for (int x_ = g_sim_member * NT; x_ < (g_sim_member + 1) * NT; x_++) \
-    for (int L = host_lane(x_), cap_ = lane_capacity(gang_live() * NT); (unsigned)L < (unsigned)(n); L += cap_)
-#define GANG_FOR_UPPER(u, n) for (int x_ = NTA; x_ < NT; x_++) \
-    for (int u = host_lane(upper_index(g_sim_member, x_)), cap_ = lane_capacity(gang_live() * NTB); (unsigned)u < (unsigned)(n); u += cap_)
-#define GANG_FOR_UPPER_FREE(it, first, n) for (int x_ = NTA; x_ < NT; x_++) \
+#define GANG_FOR(L, n) for (int x_ = g_sim_member * trk_size(HEVCE_TRK); x_ < (g_sim_member + 1) * trk_size(HEVCE_TRK); x_++) \
+    for (int L = host_lane(x_, trk_lpw(HEVCE_TRK)), cap_ = lane_capacity(gang_live() * trk_size(HEVCE_TRK), trk_lpw(HEVCE_TRK)); (unsigned)L < (unsigned)(n); L += cap_)
+#define GANG_FOR_UPPER(u, n) for (int x_ = NTA; x_ < TRK_C; x_++) \
+    for (int u = host_lane(upper_index(g_sim_member, x_), LPW), cap_ = lane_capacity(gang_live() * NTB, LPW); (unsigned)u < (unsigned)(n); u += cap_)
+#define GANG_FOR_UPPER_FREE(it, first, n) for (int x_ = NTA; x_ < TRK_C; x_++) \
     for (int st_ = 1, it = upper_free_first(upper_index(g_sim_member, x_), (first), gang_live(), (n), st_); it < (n); it += st_)
-#define TEAM_SYNC(id) sim_barrier(id)
-#define PHASE_END() sim_barrier(0)
-#define PHASE_END_T(tag) sim_barrier(0)
+#define TEAM_SYNC(id) sim_barrier(id, gang_live())
+#define PHASE_END() sim_barrier(BAR_PICTURES, gang_live())
+#define BAR_ALL() sim_barrier(BAR_PICTURES, gang_live())
 #define HEVCE_ATOMIC_OR(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
 #define HEVCE_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
 #else
+#define TEAM_A
+#define TEAM_B
+#define TEAM_JOIN() ((void)0)
 #define TEAM_SYNC(id) ((void)0)
 #define GANG_RT 1
 #define GANG_FOR(L, n) PAR_FOR(L, n)
 #define GANG_FOR_UPPER(u, n) PAR_FOR(u, n)
 #define GANG_FOR_UPPER_FREE(it, first, n) PAR_FOR(it, n)
 #define PHASE_END() ((void)0)
-#define PHASE_END_T(tag) ((void)0)
+#if !defined(HEVCE_SIM_TRACKS)
+#define BAR_ALL() ((void)0)
 #define HEVCE_ATOMIC_OR(p, v) (*(p) |= (v))
 #define HEVCE_ATOMIC_ADD(p, v) (*(p) += (v))
+#else
+#define HEVCE_ATOMIC_OR(p, v) __atomic_fetch_or((p), (v), __ATOMIC_RELAXED)
+#define HEVCE_ATOMIC_ADD(p, v) __atomic_fetch_add((p), (v), __ATOMIC_RELAXED)
 #endif
+#endif
+#endif
+#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
+#define PAR_FOR_ALL_OWNER true
 #endif
 
 struct Avail { int L, LB, A, AR; };
@@ -880,7 +940,7 @@ inline CommitShared& my_csm() { return *g_sim_csm; }
 #endif
 struct MainEnv {
     HEVCE_HD static const Tables& tables() { return my_tb(); }
-    HEVCE_HD static u8* base(int p) { return (u8*)&gang_sm(p); }   // p: picture of the gang the lane works for
+    HEVCE_HD static u8* base(int b) { return (u8*)&blk_sm(b); }   // b: shared-memory block (picture of the gang, track) the lane works for
 };
 struct CommitEnv {
     HEVCE_HD static const Tables& tables() { return my_csm().tb; }
@@ -1003,7 +1063,7 @@ template <int T> struct Dim {
 struct BSrc { int kind, off; };   // kind 0: constant 128, 1: window byte offset, 2: offset inside the candidate's edge block
 
 template <int T>
-HEVCE_HD inline void border_column(Shared& sm, const Grp& g, int j, int c0, int c1) {   // candidates [c0, c1) of a private group
+HEVCE_HD inline void border_column(Shared& sm, const Shared& pm, const Grp& g, int j, int c0, int c1) {   // candidates [c0, c1) of a private group
     constexpr int BS = Dim<T>::BS;
     const Avail& a = g.av;
     auto pos = [&](int y, int x) -> BSrc {
@@ -1038,7 +1098,7 @@ HEVCE_HD inline void border_column(Shared& sm, const Grp& g, int j, int c0, int 
     const BSrc s0 = resolve(j);
     BSrc sa = s0, sb = s0;
     if (inner) { sa = resolve(j - 1); sb = resolve(j + 1); }
-    const u8* win = sm.win;
+    const u8* win = pm.win;
     if (!g.priv) {
         auto fetch = [&](const BSrc& q) -> int { return q.kind == 1 ? win[q.off] : 128; };
         const int v = fetch(s0);
@@ -1058,12 +1118,12 @@ HEVCE_HD inline void border_column(Shared& sm, const Grp& g, int j, int c0, int 
 
 // phase A: prediction of column x (HEVCe.c:262-381), residual, forward column transform (HEVCe.c:514)
 template <int T>
-HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
+HEVCE_HD inline void phase_a_item(Shared& sm, const Shared& pm, const Grp& g, int item) {
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, BS = Dim<T>::BS, UNR = Dim<T>::UNR;
     const int c = item >> LG, x = item & (T - 1), m = g.mode0 + c;
     const int bsel = g.priv ? c : (T > 4 && use_filtered(T, m));
     const u8* B = sm.pool + g.bord + bsel * BS + 1 + 2 * T;   // B[k]: k > 0 top[k-1], k < 0 left[-k-1], 0 corner
-    const u8* org = sm.orig + g.ty * CTU + g.tx + x;
+    const u8* org = pm.orig + g.ty * CTU + g.tx + x;
     u8* pp = sm.pool + g.pred + c * (T * T) + x;
     if (x == 0) {   // per-candidate accumulators of this TU
         const int ci = g.cand0 + c;
@@ -1127,7 +1187,7 @@ HEVCE_HD inline void phase_a_item(Shared& sm, const Grp& g, int item) {
 // RD cost without the saturation tests of HEVCe.c:182-184: here dist <= 2^24 and rate <= 1.1e6, so neither product
 // nor the sum can reach 2^31 and the plain weighted sum is the same number.
 template <int T>
-HEVCE_HD inline void phase_b_item(Shared& sm, const Grp& g, int item, int q, const RdK& rk) {
+HEVCE_HD inline void phase_b_item(Shared& sm, const Shared& pm, const Grp& g, int item, int q, const RdK& rk) {
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, A2 = LG + 6;
     const int c = item >> LG, y = item & (T - 1);
     s16* bp = (s16*)(sm.pool + g.blk) + c * BLK + y * T;
@@ -1158,7 +1218,7 @@ HEVCE_HD inline void phase_b_item(Shared& sm, const Grp& g, int item, int q, con
                     const int l = lvl - t;
                     const int d1 = iabs(dl - (l << sh)) >> dsh;
                     const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
-                    const int wr = l < 6 ? sm.rate6[imax(l, 0)] : wb * (92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15));   // HEVCe.c:526-535
+                    const int wr = l < 6 ? pm.rate6[imax(l, 0)] : wb * (92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15));   // HEVCe.c:526-535
                     const int cost = wd * d + wr;
                     if (l >= 0 && cost < best) { best = cost; pick = l; }
                 }
@@ -1219,13 +1279,13 @@ HEVCE_HD inline void phase_c_item(Shared& sm, const Scratch& sc, const Grp& g, i
 
 // phase D: inverse row transform (HEVCe.c:515 with inverse=1), reconstruction, SSE (HEVCe.c:165-174)
 template <int T>
-HEVCE_HD inline void phase_d_item(Shared& sm, const Scratch& sc, const Grp& g, int item) {
+HEVCE_HD inline void phase_d_item(Shared& sm, const Shared& pm, const Scratch& sc, const Grp& g, int item) {
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK;
     const int c = item >> LG, y = item & (T - 1), ci = g.cand0 + c;
     const unsigned nzw = g.one_tu ? (sm.cgnz[ci][0] | sm.cgnz[ci][1]) : sm.cgnz[ci][g.tu];
     const s16* bp = (const s16*)(sm.pool + g.blk) + c * BLK + y * T;
     const u8* pp = sm.pool + g.pred + c * (T * T) + y * T;
-    const u8* org = sm.orig + (g.ty + y) * CTU + g.tx;
+    const u8* org = pm.orig + (g.ty + y) * CTU + g.tx;
     int v[T], o[T];
     if (nzw) {
 #pragma unroll
@@ -1262,12 +1322,13 @@ HEVCE_HD HEVCE_NOINLINE void run_borders(const Grp& gref, int off, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;   // by value: keeps the descriptor in registers instead of re-reading the caller's stack
     if (g.n == 0) return;
-    if (!g.priv) { PAR_FOR_TEAM(j, 4 * T + 1, tm, off) border_column<T>(sm, g, j, 0, 0); }
+    const Shared& pm = pic_sm();
+    if (!g.priv) { PAR_FOR_TEAM(j, 4 * T + 1, tm, off) border_column<T>(sm, pm, g, j, 0, 0); }
     else {   // private neighbours: the candidate loop of one border index is shared by four work items
         const int per = (g.n + 3) >> 2;
         PAR_FOR_TEAM(it, 4 * (4 * T + 1), tm, off) {
             const int j = it >> 2, c0 = (it & 3) * per;
-            border_column<T>(sm, g, j, c0, imin(g.n, c0 + per));
+            border_column<T>(sm, pm, g, j, c0, imin(g.n, c0 + per));
         }
     }
 }
@@ -1275,14 +1336,16 @@ template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_phase_a(const Grp& gref, int off, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;
-    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_a_item<T>(sm, g, item);
+    const Shared& pm = pic_sm();
+    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_a_item<T>(sm, pm, g, item);
 }
 template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_phase_b(const Grp& gref, int off, int q, Team tm) {
     Shared& sm = my_sm();
     const Grp g = gref;
     const RdK rk = rd_consts(q);
-    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_b_item<T>(sm, g, item, q, rk);
+    const Shared& pm = pic_sm();
+    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_b_item<T>(sm, pm, g, item, q, rk);
 }
 template <int T>
 HEVCE_HD HEVCE_NOINLINE void run_phase_c(const Scratch& scref, const Grp& gref, int off, int q, Team tm) {
@@ -1296,7 +1359,8 @@ HEVCE_HD HEVCE_NOINLINE void run_phase_d(const Scratch& scref, const Grp& gref, 
     Shared& sm = my_sm();
     const Grp g = gref;
     const Scratch sc = scref;
-    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_d_item<T>(sm, sc, g, item);
+    const Shared& pm = pic_sm();
+    PAR_FOR_TEAM(item, g.n * T, tm, off) phase_d_item<T>(sm, pm, sc, g, item);
 }
 // phase D of a group for every picture of the gang, on the upper-half threads that host no trial lane
 template <int T>
@@ -1307,7 +1371,7 @@ HEVCE_HD HEVCE_NOINLINE void run_phase_d_free(const Grp& gref, int first) {
         const int pic = it / per;
         Shared& ps = gang_sm(pic);
         const Scratch sc = ps.sc;
-        phase_d_item<T>(ps, sc, g, it - pic * per);
+        phase_d_item<T>(ps, ps, sc, g, it - pic * per);
     }
 }
 
@@ -1367,26 +1431,28 @@ HEVCE_HD inline int sm_off(const Shared& sm, const void* p) { return (int)((cons
 // One trial-coder lane: candidates 0..69 code the whole CU from the node snapshot (HEVCe.c:1434-1438, 1470-1474);
 // candidates 70..104 are NxN PU modes: residual alone from a fresh coder and fresh contexts (HEVCe.c:1505-1519).
 template <int S>
-HEVCE_HD inline void trial_lane(Shared& sm, int pic, int cand, int depth, int y0, int x0) {
+HEVCE_HD inline void trial_lane(int pic, int trk, int cand, int depth, int y0, int x0) {
+    Shared& sm = blk_sm(pic * NTRACK + trk);         // the track's block: lane contexts, candidate results, scratch
+    const Shared& pm = blk_sm(pic * NTRACK);         // the picture: maps, snapshots
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
-    const int split_ctx = (S > sm.msz[my * 9 + mx - 1]) + (S > sm.msz[(my - 1) * 9 + mx]);
-    const int pmL = sm.mpm[my * 9 + mx - 1], pmA = sm.mpm[(my - 1) * 9 + mx];
+    const int split_ctx = (S > pm.msz[my * 9 + mx - 1]) + (S > pm.msz[(my - 1) * 9 + mx]);
+    const int pmL = pm.mpm[my * 9 + mx - 1], pmA = pm.mpm[(my - 1) * 9 + mx];
     const Scratch& sc = sm.sc;
     constexpr int H = S / 2;
     const bool pu = cand >= 2 * NMODE;
     const int slot = pu ? cand - 2 * NMODE : cand;   // context-set lane
     const int step = cand / NMODE, mode = cand - step * NMODE;
-    Bac b = make_bac(sm.snap[depth]);
+    Bac b = make_bac(pm.snap[depth]);
     if (pu) coder_reset(b.c);
-    const int base_len = pu ? coder_len(b.c) : coder_len(sm.snap[depth]);
+    const int base_len = pu ? coder_len(b.c) : coder_len(pm.snap[depth]);
     if (pu) {   // a 4x4 luma TU touches last_x/y row 0 (words 4, 9), sig 0..8 (14-16), greater1 0..15 (21-24), greater2 0..3 (25)
-        const u32* src = (const u32*)sm.ctx0;
+        const u32* src = (const u32*)pm.ctx0;
         u32* dst = sm.lane_ctx + slot;
         const int W4[10] = {4, 9, 14, 15, 16, 21, 22, 23, 24, 25};
 #pragma unroll
         for (int k = 0; k < 10; k++) dst[W4[k] * NLANE] = src[W4[k]];
     } else {
-        const u32* src = (const u32*)sm.snap_ctx[depth];
+        const u32* src = (const u32*)pm.snap_ctx[depth];
         u32* dst = sm.lane_ctx + slot;
 #pragma unroll 4
         for (int k = 0; k < CTXW; k++) dst[k * NLANE] = src[k];
@@ -1401,11 +1467,11 @@ HEVCE_HD inline void trial_lane(Shared& sm, int pic, int cand, int depth, int y0
     } else {
         d.lev[0] = lev; d.mlo[0] = sm.cgnz[cand][0]; d.mhi = pu ? 0u : sm.cgnz[cand][1];
     }
-    code_cu<Bac, MainEnv>(b, pic, sm_off(sm, sm.lane_ctx + slot), 4 * NLANE, d);
+    code_cu<Bac, MainEnv>(b, pic * NTRACK + trk, sm_off(sm, sm.lane_ctx + slot), 4 * NLANE, d);
     const int bits = coder_len(b.c) - base_len;
     if (pu) sm.cand_bits[cand] = bits;
     else {   // the lane leaves its RD cost (the distortion is complete since phase D) and its end state
-        sm.cand_bits[cand] = rd_cost(rd_consts(sm.q), sm.cand_sse[cand], bits);
+        sm.cand_bits[cand] = rd_cost(rd_consts(pm.q), sm.cand_sse[cand], bits);
         cand_coder(sm)[cand] = b.c;
     }
 }
@@ -1423,7 +1489,7 @@ HEVCE_HD inline void nxn_trial(Shared& sm, int pic, int depth, int y0, int x0) {
     d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
     d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
     d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
-    code_cu<Bac, MainEnv>(b, pic, sm_off(sm, sm.nxn_ctx), 4, d);
+    code_cu<Bac, MainEnv>(b, pic * NTRACK, sm_off(sm, sm.nxn_ctx), 4, d);
     int sse = 0;
     for (int y = 0; y < 8; y++)
         for (int x = 0; x < 8; x++) { const int dd = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += dd * dd; }
@@ -1431,25 +1497,16 @@ HEVCE_HD inline void nxn_trial(Shared& sm, int pic, int depth, int y0, int x0) {
     sm.nxn_coder = b.c;
 }
 
-// Evaluate the non-split candidates of one CU node and adopt the winner (HEVCe.c:1420-1559).
+// The non-split candidates of one CU node (HEVCe.c:1420-1544): pixel rounds and trial coders.  Runs on the threads of
+// the node size's track with that track's pool / scratch; it reads the picture only outside the CU (reference samples,
+// neighbour maps) and the node's entry snapshot, so with tracks it runs while the children are being decided.
 template <int S>
-HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0, const Avail& av, int depth) {
+HEVCE_HD HEVCE_NOINLINE void eval_candidates(int q, int y0, int x0, const Avail& av, int depth) {
     Shared& sm = my_sm();
+    const Scratch sc = sm.sc;
     typedef Plan<S> P;
-    constexpr int H = S / 2, N4 = S / 4, NSTEP = S == 8 ? 3 : 2;
+    constexpr int H = S / 2;
     const RdK rk = rd_consts(q);
-    const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
-    const int gtL = S > sm.msz[my * 9 + mx - 1], gtA = S > sm.msz[(my - 1) * 9 + mx];
-    const int pmL = sm.mpm[my * 9 + mx - 1], pmA = sm.mpm[(my - 1) * 9 + mx];
-
-    // split alternative: distortion of what the children left in the window (HEVCe.c:1409-1410)
-    if (S > 8) {
-        PAR_FOR(row, S) {
-            int acc = 0;
-            for (int x = 0; x < S; x++) { const int d = (int)sm.orig[(y0 + row) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + row, x0 + x); acc += d * d; }
-            sm.part_sse[row] = acc;
-        }
-    }
 
     // ---- group descriptors (uniform over the threads of a picture)
     auto group0 = [&](int r) -> Grp {   // one-TU candidates: a slice of the 35 modes per round
@@ -1548,7 +1605,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
                 // reconstruct the candidates meanwhile (phase D of any picture of the gang)
                 GANG_FOR_UPPER(u, GANG_RT * NMODE) {
                     const int pic = u / NMODE, m = u - pic * NMODE;
-                    trial_lane<S>(gang_sm(pic), pic, 2 * NMODE + m, depth, y0, x0);
+                    trial_lane<S>(pic, 0, 2 * NMODE + m, depth, y0, x0);
                 }
                 run_phase_d_free<4>(g2, GANG_RT * NMODE);
                 TEAM_SYNC(2);
@@ -1581,12 +1638,13 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
 #if defined(HEVCE_PROFILE) && defined(__CUDA_ARCH__)
         const long long tw0_ = clock64();
 #endif
-        const int NCP = round_lanes(NC);       // every step starts on a warp boundary: one-TU, four-TU and NxN lanes run
+        const int trk = HEVCE_TRK;
+        const int NCP = round_lanes(NC, trk_lpw(trk));   // every step starts on a warp boundary: one-TU, four-TU and NxN lanes run
                                                // different code and would serialise inside a shared warp
         GANG_FOR(L, 2 * NCP + (S == 8 ? GANG_RT : 0)) {
             if (L < 2 * NCP) {
                 const int step = L >= NCP, r = L - step * NCP, pic = r / NMODE, m = r - pic * NMODE;
-                if (r < NC) trial_lane<S>(gang_sm(pic), pic, step * NMODE + m, depth, y0, x0);
+                if (r < NC) trial_lane<S>(pic, trk, step * NMODE + m, depth, y0, x0);
             } else nxn_trial(gang_sm(L - 2 * NCP), L - 2 * NCP, depth, y0, x0);
         }
 #if defined(HEVCE_PROFILE) && defined(__CUDA_ARCH__)
@@ -1599,6 +1657,27 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
 #endif
     }
     PHASE_END_T(P_TRIAL);
+}
+
+// Decision of one CU node and adoption of the winner (HEVCe.c:1440, 1476, 1546-1559), on track 0; `cm` is the block of
+// the track that evaluated the node's candidates.
+template <int S>
+HEVCE_HD HEVCE_NOINLINE void decide_adopt(int q, int y0, int x0, int depth) {
+    Shared& sm = my_sm();
+    Shared& cm = blk_sm(HEVCE_SLOT * NTRACK + TrackOf<S>::value);
+    const Scratch sc = cm.sc;
+    constexpr int N4 = S / 4;
+    const RdK rk = rd_consts(q);
+    const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
+    // split alternative: distortion of what the children left in the window (HEVCe.c:1409-1410)
+    if (S > 8) {
+        PAR_FOR(row, S) {
+            int acc = 0;
+            for (int x = 0; x < S; x++) { const int d = (int)sm.orig[(y0 + row) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + row, x0 + x); acc += d * d; }
+            sm.part_sse[row] = acc;
+        }
+        PHASE_END_T(P_DECIDE);
+    }
 
     // ---- decision, reference order; every comparison is ">=" so the last minimum wins
     PAR_FOR(one, 1) {
@@ -1609,7 +1688,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             best = rd_cost(rk, sse, coder_len(sm.live) - coder_len(sm.snap[depth]));
         }
         for (int c = 0; c < 2 * NMODE; c++) {   // one-TU modes 0..34, then four-TU modes 0..34 (HEVCe.c:1440, 1476)
-            const int cost = sm.cand_bits[c];   // RD cost, left by the candidate's trial lane
+            const int cost = cm.cand_bits[c];   // RD cost, left by the candidate's trial lane
             if (best >= cost) { best = cost; win = c; }
         }
         if (S == 8 && best >= sm.nxn_cost) win = NCAND;   // HEVCe.c:1546
@@ -1640,7 +1719,7 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             HEVCE_WIN(sm, y0 + i / S, x0 + i % S) = rp[i];
             clev[i] = lp[i];
         }
-        PAR_FOR(i, CTXW) ((u32*)sm.live_ctx)[i] = sm.lane_ctx[i * NLANE + win];
+        PAR_FOR(i, CTXW) ((u32*)sm.live_ctx)[i] = cm.lane_ctx[i * NLANE + win];
         PAR_FOR(i, N4 * N4) {
             const int idx = (my + i / N4) * 9 + mx + i % N4;
             sm.msz[idx] = (u8)S;
@@ -1650,9 +1729,16 @@ HEVCE_HD HEVCE_NOINLINE void eval_node(const Scratch& sc, int q, int y0, int x0,
             const int n8 = S / 8;
             sm.kind[((y0 >> 3) + i / n8) * 4 + (x0 >> 3) + i % n8] = (u8)step;
         }
-        PAR_FOR(one, 1) sm.live = cand_coder(sm)[win];
+        PAR_FOR(one, 1) sm.live = cand_coder(cm)[win];
     }
     PHASE_END_T(P_ADOPT);
+}
+
+// without tracks: a node's candidates and its decision by the same threads, after its children
+template <int S>
+HEVCE_HD inline void eval_node(int q, int y0, int x0, const Avail& av, int depth) {
+    eval_candidates<S>(q, y0, x0, av, depth);
+    decide_adopt<S>(q, y0, x0, depth);
 }
 
 // enter a node: snapshot the live state (HEVCe.c:1364-1365) and, for splittable nodes, code split_cu_flag = 1
@@ -1775,71 +1861,102 @@ HEVCE_HD inline int write_header(u8* out, int q, int H, int W) {
 // ------------------------------------------------------------------------------------------------------------
 // one picture (HEVCe.c:1570-1647)
 // ------------------------------------------------------------------------------------------------------------
-HEVCE_HD inline void encode_picture(const Job& job, Shared& sm, const Scratch& sc) {
+// `scs`: the global scratch of this picture slot, one set per track
+HEVCE_HD inline void encode_picture(const Job& job, const Scratch* scs) {
+    Shared& sm = pic_sm();
+    const Scratch sc = scs[0];
     const int q = job.q, H = job.H, W = job.W;
-    PAR_FOR(i, 4 * CTXW) {
+#define PIC_FOR(item, n) if (PAR_FOR_ALL_OWNER) PAR_FOR_ALL(item, n)   /* picture-wide phase: all threads of the picture */
+    PIC_FOR(i, 4 * CTXW) {
         const u8 v = ctx_init_value(my_tb().ctx_iv[i], q);
         sm.ctx0[i] = v;
         sm.live_ctx[i] = v;
     }
-    PAR_FOR(i, 81) { sm.msz[i] = CTU; sm.mpm[i] = 1; }
-    PAR_FOR(i, W / 4) sc.msz_line[i] = CTU;
-    PAR_FOR(lvl, 6) {
+    PIC_FOR(i, 81) { sm.msz[i] = CTU; sm.mpm[i] = 1; }
+    PIC_FOR(i, W / 4) sc.msz_line[i] = CTU;
+    PIC_FOR(lvl, 6) {
         const RdK rk = rd_consts(q);
         sm.rate6[lvl] = rk.wb * (lvl == 0 ? 0 : lvl == 1 ? 70000 : lvl == 2 ? 90000 : lvl == 3 ? 92000 : lvl == 4 ? 157536 : 190304);   // HEVCe.c:527
     }
-    PAR_FOR(one, 1) {
+    PIC_FOR(t, NTRACK) blk_sm(HEVCE_SLOT * NTRACK + t).sc = scs[t];
+    PIC_FOR(one, 1) {
         coder_reset(sm.live);
         sm.error = 0;
-        sm.sc = sc;
         sm.q = q;
         sm.stream_pos = write_header(job.out, q, H, W);
     }
-    PHASE_END_T(P_MISC);
+    BAR_ALL();
 
     int ctu_idx = 0;
     for (int cy = 0; cy < H; cy += CTU) {
         for (int cx = 0; cx < W; cx += CTU, ctu_idx++) {
             const Avail av = {cx > 0, 0, cy > 0, cy > 0 && cx + CTU < W};   // HEVCe.c:1606-1609
             // ---- load: original (edge-replicated), neighbour samples, neighbour maps
-            PAR_FOR(i, CTU * CTU) {
+            PIC_FOR(i, CTU * CTU) {
                 const int y = imin(cy + i / CTU, job.src_h - 1), x = imin(cx + i % CTU, job.src_w - 1);
                 sm.orig[i] = job.img[(size_t)y * job.src_w + x];
             }
-            PAR_FOR(i, CTU) sm.win[(1 + i) * WP] = cx > 0 ? job.rcon[(size_t)(cy + i) * W + cx - 1] : (u8)0;
-            PAR_FOR(j, 2 * CTU + 1) sm.win[j] = cy > 0 ? job.rcon[(size_t)(cy - 1) * W + iclip(cx - 1 + j, 0, W - 1)] : (u8)0;
-            PAR_FOR(i, 8) {
+            PIC_FOR(i, CTU) sm.win[(1 + i) * WP] = cx > 0 ? job.rcon[(size_t)(cy + i) * W + cx - 1] : (u8)0;
+            PIC_FOR(j, 2 * CTU + 1) sm.win[j] = cy > 0 ? job.rcon[(size_t)(cy - 1) * W + iclip(cx - 1 + j, 0, W - 1)] : (u8)0;
+            PIC_FOR(i, 8) {
                 sm.msz[i + 1] = sc.msz_line[cx / 4 + i];                               // above row: CU sizes scroll,
                 sm.mpm[i + 1] = 1;                                                     // modes stay DC (HEVCe.c:1634-1637)
                 sm.msz[(i + 1) * 9] = cx > 0 ? sm.msz[(i + 1) * 9 + 8] : (u8)CTU;      // left column = previous CTU's last column
                 sm.mpm[(i + 1) * 9] = cx > 0 ? sm.mpm[(i + 1) * 9 + 8] : (u8)1;
             }
             CtuRec& rec = job.recs[ctu_idx];
-            PAR_FOR(i, CTXW) ((u32*)rec.ctx)[i] = ((const u32*)sm.live_ctx)[i];
-            PAR_FOR(one, 1) { sm.live.n = 0; rec.start = sm.live; sm.ctu_lev = job.levs + (size_t)ctu_idx * (CTU * CTU); }
-            PHASE_END_T(P_LOAD);
+            PIC_FOR(i, CTXW) ((u32*)rec.ctx)[i] = ((const u32*)sm.live_ctx)[i];
+            PIC_FOR(one, 1) { sm.live.n = 0; rec.start = sm.live; sm.ctu_lev = job.levs + (size_t)ctu_idx * (CTU * CTU); }
+            BAR_ALL();
 
-            // ---- CU quadtree, z-order, children before the parent's own candidates (HEVCe.c:1403-1413)
-            enter_node<32>(sm, 0, 0, 0);
-            for (int a = 0; a < 4; a++) {
-                const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
-                const Avail av16 = sub_avail(av, a);
-                enter_node<16>(sm, y16, x16, 1);
-                for (int c = 0; c < 4; c++) {
-                    const int y8 = y16 + (c >> 1) * 8, x8 = x16 + (c & 1) * 8;
-                    enter_node<8>(sm, y8, x8, 2);
-                    eval_node<8>(sc, q, y8, x8, sub_avail(av16, c), 2);
+            // ---- CU quadtree, z-order (HEVCe.c:1403-1413)
+            if (!TRACKS) {   // children before the parent's own candidates, everything on the same threads
+                enter_node<32>(sm, 0, 0, 0);
+                for (int a = 0; a < 4; a++) {
+                    const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
+                    const Avail av16 = sub_avail(av, a);
+                    enter_node<16>(sm, y16, x16, 1);
+                    for (int c = 0; c < 4; c++) {
+                        const int y8 = y16 + (c >> 1) * 8, x8 = x16 + (c & 1) * 8;
+                        enter_node<8>(sm, y8, x8, 2);
+                        eval_node<8>(q, y8, x8, sub_avail(av16, c), 2);
+                    }
+                    eval_node<16>(q, y16, x16, av16, 1);
                 }
-                eval_node<16>(sc, q, y16, x16, av16, 1);
+                eval_node<32>(q, 0, 0, av, 0);
+            } else {
+                // Parent || child: as soon as a node's entry snapshot exists (rendezvous), its own candidates are evaluated
+                // on the node size's track while track 0 walks the children; the decision waits for both (second rendezvous).
+                ON_TRACK(0) enter_node<32>(sm, 0, 0, 0);
+                TRACK_RDV(2);
+                ON_TRACK(2) eval_candidates<32>(q, 0, 0, av, 0);
+                for (int a = 0; a < 4; a++) {
+                    const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
+                    const Avail av16 = sub_avail(av, a);
+                    ON_TRACK(0) enter_node<16>(sm, y16, x16, 1);
+                    TRACK_RDV(1);
+                    ON_TRACK(1) eval_candidates<16>(q, y16, x16, av16, 1);
+                    ON_TRACK(0) {
+                        for (int c = 0; c < 4; c++) {
+                            const int y8 = y16 + (c >> 1) * 8, x8 = x16 + (c & 1) * 8;
+                            enter_node<8>(sm, y8, x8, 2);
+                            eval_node<8>(q, y8, x8, sub_avail(av16, c), 2);
+                        }
+                    }
+                    TRACK_RDV(1);
+                    ON_TRACK(0) decide_adopt<16>(q, y16, x16, 1);
+                }
+                TRACK_RDV(2);
+                ON_TRACK(0) decide_adopt<32>(q, 0, 0, 0);
+                BAR_ALL();
             }
-            eval_node<32>(sc, q, 0, 0, av, 0);
 
             // ---- store reconstruction + map row, terminate bin, commit the CTU's bytes
-            PAR_FOR(i, CTU * CTU) job.rcon[(size_t)(cy + i / CTU) * W + cx + i % CTU] = HEVCE_WIN(sm, i / CTU, i % CTU);
-            PAR_FOR(i, 8) sc.msz_line[cx / 4 + i] = sm.msz[8 * 9 + 1 + i];
-            PAR_FOR(i, 81) { rec.msz[i] = sm.msz[i]; rec.mpm[i] = sm.mpm[i]; }
-            PAR_FOR(i, 16) rec.kind[i] = sm.kind[i];
-            PAR_FOR(one, 1) {
+            PIC_FOR(i, CTU * CTU) job.rcon[(size_t)(cy + i / CTU) * W + cx + i % CTU] = HEVCE_WIN(sm, i / CTU, i % CTU);
+            PIC_FOR(i, 8) sc.msz_line[cx / 4 + i] = sm.msz[8 * 9 + 1 + i];
+            PIC_FOR(i, 81) { rec.msz[i] = sm.msz[i]; rec.mpm[i] = sm.mpm[i]; }
+            PIC_FOR(i, 16) rec.kind[i] = sm.kind[i];
+            PIC_FOR(one, 1) {
                 const int last = cy + CTU >= H && cx + CTU >= W;
                 Bac t = make_bac(sm.live);
                 t.put_terminate(last);                                                  // HEVCe.c:1630
@@ -1850,14 +1967,15 @@ HEVCE_HD inline void encode_picture(const Job& job, Shared& sm, const Scratch& s
                 sm.stream_pos += t.c.n;                                                 // bytes the commit pass will write
                 sm.live = t.c;
             }
-            PHASE_END_T(P_COMMIT);
+            BAR_ALL();
         }
     }
-    PAR_FOR(one, 1) {
+    PIC_FOR(one, 1) {
         job.result[0] = sm.stream_pos;
         if (sm.error) HEVCE_ATOMIC_OR(job.result + 1, sm.error);
     }
-    PHASE_END_T(P_MISC);
+    BAR_ALL();
+#undef PIC_FOR
 }
 
 }   // namespace HEVCE_NS

@@ -132,7 +132,7 @@ void variants_init() {
     std::call_once(g_variants_once, [] {
         fill_tables(g_host_tables);
         // relative per-CTU latency of a gang (all SMs busy with the same variant), measured on B200 -- profiles/r2_notes.md
-        static const double kCost[NVARIANT] = {1.00, 0.62, 0.42, 0.30};
+        static const double kCost[NVARIANT] = {1.00, 0.79, 0.68, 0.59, 0.58};   // 9.25 / 7.28 / 6.25 / 5.42 ms per CTU, 148 gangs of 64x64 pictures, qpd6=2
         for (int v = 0; v < NVARIANT; v++) { g_variants[v].info(&g_variants[v].vi); g_variants[v].cost = kCost[v]; }
         if (const char* env = getenv("HEVCE_VARIANT"))
             for (int v = 0; v < NVARIANT; v++) if (!strcmp(env, g_variants[v].name)) g_forced_variant = v;
@@ -329,7 +329,7 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     if ((rc = grow(&s->d_order, &s->c_order, gangs.size()))) return rc;
     if ((rc = grow(&s->d_results, &s->c_results, (size_t)2 * n))) return rc;
     if (!s->d_counter) CK(cudaMalloc((void**)&s->d_counter, sizeof(int)));
-    const size_t g = (size_t)s->grid * GANGV, nlev = (size_t)NCAND * LEV_STRIDE + 64, nrec = (size_t)NREC * CTU * CTU;
+    const size_t g = (size_t)s->grid * GANGV * g_variants[best].vi.tracks, nlev = (size_t)NCAND * LEV_STRIDE + 64, nrec = (size_t)NREC * CTU * CTU;
     s->line_pitch = maxW / 4 + 32;
     if ((rc = grow(&s->d_glev, &s->c_glev, g * nlev))) return rc;
     if ((rc = grow(&s->d_grec, &s->c_grec, g * nrec))) return rc;

@@ -27,15 +27,14 @@ __device__ unsigned long long g_phase_count[128];
 }
 #endif
 
-static constexpr size_t kSmemBytes = GANG * sizeof(Shared) + sizeof(Tables) + sizeof(GangCtl);
+static constexpr size_t kSmemBytes = NBLOCK * sizeof(Shared) + sizeof(Tables) + sizeof(GangCtl);
 
 // `gangs` lists GANG job indices per work unit, live pictures first, -1 for the empty slots of a short gang.
 __global__ void __launch_bounds__(NT * GANG, 1)
 VSYM(hevce_encode_kernel_)(const Job* __restrict__ jobs, const int* __restrict__ gangs, int ngangs, const Scratch* __restrict__ slots,
                            int* counter, const Tables* __restrict__ tables) {
     const int member = threadIdx.x / NT;
-    Shared& sm = my_sm();
-    const Scratch sc = slots[blockIdx.x * GANG + member];
+    const Scratch* scs = slots + (size_t)(blockIdx.x * GANG + member) * NTRACK;   // this picture slot's scratch, one set per track
     for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += NT * GANG) ((u32*)&my_tb())[i] = ((const u32*)tables)[i];
     for (;;) {
         if (threadIdx.x == 0) {
@@ -51,7 +50,7 @@ VSYM(hevce_encode_kernel_)(const Job* __restrict__ jobs, const int* __restrict__
         __syncthreads();
         if (k >= ngangs) break;
         // the threads of an empty slot go straight to the queue barrier; the live pictures synchronise among themselves
-        if (member < live) encode_picture(jobs[gangs[k * GANG + member]], sm, sc);
+        if (member < live) encode_picture(jobs[gangs[k * GANG + member]], scs);
     }
 }
 
@@ -71,6 +70,7 @@ extern "C" void VSYM(hevce_variant_info_)(hevce_variant_info* out) {
     out->threads_per_picture = NT;
     out->lanes_per_warp = LPW;
     out->wide = WIDE ? 1 : 0;
+    out->tracks = NTRACK;
     out->smem_bytes = (long long)kSmemBytes;
 }
 

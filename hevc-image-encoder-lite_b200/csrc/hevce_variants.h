@@ -7,6 +7,7 @@ typedef struct hevce_variant_info {
     int threads_per_picture;   /* CTA size = gang * threads_per_picture              */
     int lanes_per_warp;        /* trial-coder lanes hosted by one warp               */
     int wide;                  /* 1: one picture per CTA with the large pool         */
+    int tracks;                /* thread tracks per picture (3 = parent || child)    */
     long long smem_bytes;      /* dynamic shared memory per CTA                      */
 } hevce_variant_info;
 
@@ -15,7 +16,8 @@ typedef struct hevce_variant_info {
     X(g7, 7, 128, 32, 0)      \
     X(g4, 4, 224, 16, 0)      \
     X(g2, 2, 448, 8, 0)       \
-    X(w1, 1, 896, 4, 1)
+    X(w1, 1, 896, 4, 1)       \
+    X(t1, 1, 896, 6, 0)
 
 #ifdef __cplusplus
 extern "C" {

@@ -8,7 +8,14 @@
 
 #include "hevce_core.h"
 
-namespace HEVCE_NS { int g_sim_order = 0; Shared* g_sim_sm = nullptr; Tables* g_sim_tb = nullptr; CommitShared* g_sim_csm = nullptr; }
+namespace HEVCE_NS {
+int g_sim_order = 0, g_sim_nlive = 1;
+Shared* g_sim_sms = nullptr;
+Tables* g_sim_tb = nullptr;
+CommitShared* g_sim_csm = nullptr;
+thread_local int g_sim_member = 0, g_sim_trk = 0;
+void sim_barrier(int, int) {}
+}
 
 static std::vector<HEVCE_NS::CtuRec> g_last_recs;
 static int g_last_h = 0, g_last_w = 0;
@@ -27,18 +34,23 @@ extern "C" int hevce_sim_encode(unsigned char* out, int out_cap, const unsigned 
     job.W = (imin(*xsz, max_dim) + CTU - 1) / CTU * CTU;
     job.q = q; job.out_cap = out_cap;
     const int nctu = (job.H / CTU) * (job.W / CTU);
-    std::vector<s16> glev((size_t)NCAND * LEV_STRIDE + 16), lev((size_t)nctu * CTU * CTU);
+    std::vector<s16> lev((size_t)nctu * CTU * CTU);
     std::vector<CtuRec> recs(nctu);
     job.recs = recs.data(); job.levs = lev.data();
-    std::vector<u8> grec((size_t)NREC * CTU * CTU), line(job.W / 4 + 8);
-    Scratch sc;
-    sc.glev = glev.data(); sc.grec = grec.data(); sc.msz_line = line.data();
-    Shared* sm = new Shared;
-    memset(sm, 0xA5, sizeof(Shared));   // shared memory is not zeroed on the GPU either
-    g_sim_sm = sm;
+    std::vector<std::vector<s16>> glev(NTRACK);
+    std::vector<std::vector<u8>> grec(NTRACK), line(NTRACK);
+    Scratch sc[NTRACK];
+    for (int t = 0; t < NTRACK; t++) {   // one scratch set per track (the tracks run one after the other here)
+        glev[t].resize((size_t)NCAND * LEV_STRIDE + 16); grec[t].resize((size_t)NREC * CTU * CTU); line[t].resize(job.W / 4 + 8);
+        sc[t].glev = glev[t].data(); sc[t].grec = grec[t].data(); sc[t].msz_line = line[t].data();
+    }
+    Shared* sm = new Shared[NTRACK];
+    memset(sm, 0xA5, sizeof(Shared) * NTRACK);   // shared memory is not zeroed on the GPU either
+    g_sim_sms = sm;
     g_sim_tb = &tables;
-    encode_picture(job, *sm, sc);
-    delete sm;
+    g_sim_trk = 0;
+    encode_picture(job, sc);
+    delete[] sm;
     // commit pass (hevce_commit_kernel on the GPU): one CTU at a time here
     CommitShared* cs = new CommitShared;
     memset(cs, 0x5A, sizeof(CommitShared));

@@ -19,9 +19,9 @@ int g_sim_nlive = 1;
 Shared* g_sim_sms = nullptr;
 Tables* g_sim_tb = nullptr;
 CommitShared* g_sim_csm = nullptr;
-thread_local int g_sim_member = 0;
-static pthread_barrier_t g_bar[3];
-void sim_barrier(int id) { pthread_barrier_wait(&g_bar[id]); }
+thread_local int g_sim_member = 0, g_sim_trk = 0;
+static pthread_barrier_t g_bar[4];   // 1 / 2: the teams, 3: the live pictures
+void sim_barrier(int id, int) { pthread_barrier_wait(&g_bar[id]); }
 }   // namespace HEVCE_NS
 
 // Encode `n` (1..GANG) pictures of identical size h x w as ONE gang (the slots of a short gang stay empty: only the live
@@ -55,15 +55,16 @@ extern "C" int hevce_simgang_encode(int n, unsigned char* const* outs, int out_c
     memset(sms, 0xA5, sizeof(Shared) * GANG);
     g_sim_sms = sms;
     g_sim_nlive = n;
-    for (int b = 0; b < 3; b++) pthread_barrier_init(&g_bar[b], nullptr, n);
+    for (int b = 0; b < 4; b++) pthread_barrier_init(&g_bar[b], nullptr, n);
     std::vector<std::thread> th;
     for (int m = 0; m < n; m++)
         th.emplace_back([&, m] {
             g_sim_member = m;
-            encode_picture(jobs[m], sms[m], sc[m]);
+            g_sim_trk = 0;
+            encode_picture(jobs[m], &sc[m]);
         });
     for (auto& t : th) t.join();
-    for (int b = 0; b < 3; b++) pthread_barrier_destroy(&g_bar[b]);
+    for (int b = 0; b < 4; b++) pthread_barrier_destroy(&g_bar[b]);
     free(sms);
     CommitShared* cs = new CommitShared;
     memset(cs, 0x5A, sizeof(CommitShared));

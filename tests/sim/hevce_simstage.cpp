@@ -1,0 +1,105 @@
+// hevce_simstage.cpp -- TEST INFRASTRUCTURE ONLY: single stages of the kernel source (csrc/hevce_core.h) on the host, so
+// that each can be compared with the function of the reference that it replaces (tests/test_stages.py calls the
+// reference's exported getBorder / predict / transform / quantize / deQuantize / putCoef + CABAClen through ctypes):
+//   hevce_stage_pixel    : reference samples -> prediction -> residual -> forward transform -> RDOQ -> group zero-out ->
+//                          dequantisation -> inverse transform -> reconstruction + SSE of ONE candidate (phases border, A-D)
+//   hevce_stage_residual : residual_coding() of one TU from a fresh coder and fresh contexts (put_residual)
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "hevce_core.h"
+
+namespace HEVCE_NS {
+int g_sim_order = 0, g_sim_nlive = 1;
+Shared* g_sim_sms = nullptr;
+Tables* g_sim_tb = nullptr;
+CommitShared* g_sim_csm = nullptr;
+thread_local int g_sim_member = 0, g_sim_trk = 0;
+void sim_barrier(int, int) {}
+}   // namespace HEVCE_NS
+
+using namespace HEVCE_NS;
+
+static Tables* tables() {
+    static Tables t;
+    static bool done = false;
+    if (!done) { fill_tables(t); done = true; }
+    return &t;
+}
+
+template <int T>
+static void pixel(Shared& sm, const Scratch& sc, int mode, int q, int ty, int tx, const Avail& av) {
+    Grp g;
+    g.n = 1; g.cand0 = 0; g.mode0 = mode; g.ty = ty; g.tx = tx; g.av = av; g.priv = 0;
+    g.cuy = ty; g.cux = tx; g.cus = T; g.tu = 0; g.one_tu = 1; g.grec = 1;
+    g.blk = 0; g.pred = 4096; g.psum = 6144; g.bord = 12288; g.rec = -1; g.rec_stride = 0; g.rec_pitch = 0;
+    const RdK rk = rd_consts(q);
+    for (int j = 0; j <= 4 * T; j++) border_column<T>(sm, sm, g, j, 0, 0);
+    for (int i = 0; i < T; i++) phase_a_item<T>(sm, sm, g, i);
+    for (int i = 0; i < T; i++) phase_b_item<T>(sm, sm, g, i, q, rk);
+    for (int i = 0; i < T; i++) phase_c_item<T>(sm, sc, g, i, q);
+    for (int i = 0; i < T; i++) phase_d_item<T>(sm, sm, sc, g, i);
+}
+
+// win: the (CTU+1) x WP reconstruction window (row 0 / column 0 = neighbours outside the CTU), orig: the CTU's 32x32
+// original; the TU of size T sits at (ty, tx) inside the CTU.  Outputs: pred / rec T*T raster, lev T*T raster (int).
+extern "C" int hevce_stage_pixel(int T, int mode, int q, const unsigned char* win, const unsigned char* orig, int ty, int tx,
+                                 int aL, int aLB, int aA, int aAR, unsigned char* pred, int* lev, unsigned char* rec, int* sse) {
+    Shared* sm = new Shared[NTRACK];
+    memset(sm, 0x5c, sizeof(Shared) * NTRACK);
+    g_sim_sms = sm; g_sim_tb = tables(); g_sim_trk = 0; g_sim_member = 0;
+    memcpy(sm->win, win, sizeof(sm->win));
+    memcpy(sm->orig, orig, sizeof(sm->orig));
+    const RdK rk = rd_consts(q);
+    for (int l = 0; l < 6; l++) sm->rate6[l] = rk.wb * (l == 0 ? 0 : l == 1 ? 70000 : l == 2 ? 90000 : l == 3 ? 92000 : l == 4 ? 157536 : 190304);
+    std::vector<s16> glev((size_t)NCAND * LEV_STRIDE + 16);
+    std::vector<u8> grec((size_t)NREC * CTU * CTU);
+    Scratch sc;
+    sc.glev = glev.data(); sc.grec = grec.data(); sc.msz_line = nullptr;
+    const Avail av = {aL, aLB, aA, aAR};
+    if (T == 4) pixel<4>(*sm, sc, mode, q, ty, tx, av);
+    else if (T == 8) pixel<8>(*sm, sc, mode, q, ty, tx, av);
+    else if (T == 16) pixel<16>(*sm, sc, mode, q, ty, tx, av);
+    else pixel<32>(*sm, sc, mode, q, ty, tx, av);
+    memcpy(pred, sm->pool + 4096, (size_t)T * T);
+    memcpy(rec, grec.data(), (size_t)T * T);
+    // levels: groups in raster order, the 16 levels of a group in the scan order of the mode -> raster
+    const int st = scan_type(T, mode), ncg = T / 4;
+    for (int gy = 0; gy < ncg; gy++)
+        for (int gx = 0; gx < ncg; gx++)
+            for (int k = 0; k < 16; k++) {
+                const int p4 = tables()->scan4[st][k];
+                lev[(gy * 4 + (p4 >> 2)) * T + gx * 4 + (p4 & 3)] = glev[(gy * ncg + gx) * 16 + k];
+            }
+    *sse = sm->cand_sse[0];
+    delete[] sm;
+    return 0;
+}
+
+// lev: T*T raster levels.  state: {range, low, nbits, nbytes, held, z, n} at the end.  returns the bits written.
+extern "C" int hevce_stage_residual(int T, int mode, int q, const int* lev, int* state) {
+    const Tables& tb = *tables();
+    g_sim_tb = tables();
+    u8 ctx[4 * CTXW];
+    for (int i = 0; i < 4 * CTXW; i++) ctx[i] = ctx_init_value(tb.ctx_iv[i], q);
+    const int st = scan_type(T, mode), ncg = T / 4;
+    std::vector<s16> blocked((size_t)T * T + 16);
+    unsigned mlo = 0, mhi = 0;
+    for (int gy = 0; gy < ncg; gy++)
+        for (int gx = 0; gx < ncg; gx++)
+            for (int k = 0; k < 16; k++) {
+                const int p4 = tb.scan4[st][k];
+                const int v = lev[(gy * 4 + (p4 >> 2)) * T + gx * 4 + (p4 & 3)];
+                blocked[(gy * ncg + gx) * 16 + k] = (s16)v;
+                if (v) { const int b = gy * 8 + gx; if (b < 32) mlo |= 1u << b; else mhi |= 1u << (b - 32); }
+            }
+    Bac b;
+    coder_reset(b.c);
+    b.out = nullptr; b.cap = 0;
+    const int len0 = coder_len(b.c);
+    const Cx cx = {ctx, 4};
+    put_residual(b, tb, cx, T, mode, blocked.data(), mlo, mhi);
+    state[0] = b.c.range; state[1] = b.c.low; state[2] = b.c.nbits; state[3] = b.c.nbytes; state[4] = b.c.held; state[5] = b.c.z; state[6] = b.c.n;
+    return coder_len(b.c) - len0;
+}

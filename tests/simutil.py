@@ -13,12 +13,13 @@ _u8p = ctypes.POINTER(ctypes.c_ubyte)
 
 
 # kernel variants (csrc/Makefile, hevce_variants.h): tag -> (pictures per CTA, threads per picture, lanes per warp, wide)
-VARIANTS = {"g7": (7, 128, 32, 0), "g4": (4, 224, 16, 0), "g2": (2, 448, 8, 0), "w1": (1, 896, 4, 1)}
+VARIANTS = {"g7": (7, 128, 32, 0), "g4": (4, 224, 16, 0), "g2": (2, 448, 8, 0), "w1": (1, 896, 4, 1), "t1": (1, 896, 6, 0)}
+TRACK_FLAGS = {"t1": ["-DHEVCE_OPT_TRACKS=1", "-DHEVCE_OPT_TRK_C=448", "-DHEVCE_OPT_LPW_P=12"]}   # parent || child variants
 
 
 def variant_flags(variant):
     g, nt, lpw, wide = VARIANTS[variant]
-    return [f"-DHEVCE_OPT_GANG={g}", f"-DHEVCE_OPT_NT={nt}", f"-DHEVCE_OPT_LPW={lpw}", f"-DHEVCE_OPT_WIDE={wide}"]
+    return [f"-DHEVCE_OPT_GANG={g}", f"-DHEVCE_OPT_NT={nt}", f"-DHEVCE_OPT_LPW={lpw}", f"-DHEVCE_OPT_WIDE={wide}"] + TRACK_FLAGS.get(variant, [])
 
 
 def _build(src, so, variant, extra=()):
@@ -107,3 +108,30 @@ def simgang_encode(imgs, qs, order=0, variant="g7"):
     rc = simgang(variant).hevce_simgang_encode(n, arr(outs), cap, arr(imgs), arr(rcons), h, w, qa, int(order), lens, errs)
     assert rc == 0
     return [(outs[i][: lens[i]].tobytes(), rcons[i], errs[i]) for i in range(n)]
+
+
+# ---- track simulator: one host thread per track of a parent || child variant (tests/sim/hevce_simtrack.cpp)
+_tlibs = {}
+
+
+def build_simtrack(variant="t1"):
+    so = os.path.join(SIM_DIR, f"libhevce_simtrack_{variant}.so")
+    _build("hevce_simtrack.cpp", so, variant, extra=("-pthread",))
+    return so
+
+
+def simtrack_encode(img, q, order=0, variant="t1"):
+    if variant not in _tlibs:
+        L = ctypes.CDLL(build_simtrack(variant))
+        L.hevce_simtrack_encode.restype = ctypes.c_int
+        _tlibs[variant] = L
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    hp, wp = (h + 31) // 32 * 32, (w + 31) // 32 * 32
+    rcon = np.zeros((hp, wp), np.uint8)
+    cap = 256 + 2 * hp * wp
+    out = np.zeros(cap, np.uint8)
+    ys, xs, err = ctypes.c_int(h), ctypes.c_int(w), ctypes.c_int(0)
+    n = _tlibs[variant].hevce_simtrack_encode(out.ctypes.data_as(_u8p), cap, img.ctypes.data_as(_u8p), rcon.ctypes.data_as(_u8p),
+                                             ctypes.byref(ys), ctypes.byref(xs), int(q), int(order), ctypes.byref(err))
+    return out[:n].tobytes(), rcon, err.value

@@ -59,14 +59,15 @@ def test_concurrent_callers(H):
     results; a batch call runs beside them."""
     data, _ = G.small_cases()
     cases = [("k01_45x70", 2), ("noise_64", 0), ("k01_64x128", 4), ("k01_33x97", 1), ("checker2_64", 3), ("k01_96x64", 2)]
-    want = {c: (data[f"{c[0]}/q{c[1]}/stream"].tobytes(), data[f"{c[0]}/q{c[1]}/rcon"]) for c in cases}
+    want = {c: (data[f"{c[0]}/q{c[1]}/stream"].tobytes(), np.array(data[f"{c[0]}/q{c[1]}/rcon"])) for c in cases}
+    inputs = {c: np.array(data[f"{c[0]}/in"]) for c in cases}     # materialised: the npz reader is not thread-safe
     errors = []
 
     def worker(k):
         try:
             for rep in range(3):
                 for c in cases[k % 2::2] if k < 4 else cases:
-                    s, r = H.HEVCImageEncoder(data[f"{c[0]}/in"], c[1])
+                    s, r = H.HEVCImageEncoder(inputs[c], c[1])
                     if s != want[c][0] or not np.array_equal(r, want[c][1]):
                         errors.append((k, c))
         except Exception as e:   # noqa: BLE001
@@ -74,7 +75,7 @@ def test_concurrent_callers(H):
 
     def batch_worker():
         try:
-            s, r = H.HEVCImageEncoderBatch([data[f"{c[0]}/in"] for c in cases], [c[1] for c in cases])
+            s, r = H.HEVCImageEncoderBatch([inputs[c] for c in cases], [c[1] for c in cases])
             for c, a, b in zip(cases, s, r):
                 if a != want[c][0] or not np.array_equal(b, want[c][1]):
                     errors.append(("batch", c))

@@ -103,3 +103,52 @@ def test_wide_variant_single_thread_simulator_permuted():
         s, r, err = S.sim_encode(img, q, order, variant="w1")
         so, ro = R.oracle_encode(img, q)
         assert err == 0 and s == so and np.array_equal(r, ro), (q, order)
+
+
+def test_track_simulator_matches_oracle():
+    """Parent || child variant t1: one host thread per track, real rendezvous; a 64x96 crop and a padded 45x70 picture
+    at every qpd6 against the oracle."""
+    for k, (h, w) in enumerate(((64, 96), (45, 70))):
+        img = crops(1, h, w)[0]
+        for q in range(5):
+            s, r, err = S.simtrack_encode(img, q, order=(0, 3)[(q + k) % 2])
+            so, ro = R.oracle_encode(img, q)
+            assert err == 0 and s == so and np.array_equal(r, ro), (h, w, q)
+            s1, r1, e1 = S.sim_encode(img, q, variant="t1")      # the same variant with its tracks one after the other
+            assert (s1, e1) == (s, err) and np.array_equal(r1, r)
+
+
+def test_tracks_share_no_unsynchronised_data_under_thread_sanitizer(tmp_path):
+    """ThreadSanitizer over the track simulator: the 16x16 / 32x32 candidate tracks run beside the 8x8 chain."""
+    probe = tmp_path / "probe.cpp"
+    probe.write_text("#include <thread>\nint x;int main(){std::thread a([]{for(int i=0;i<100000;i++)x++;});"
+                     "std::thread b([]{for(int i=0;i<100000;i++)x++;});a.join();b.join();return 0;}\n")
+    if subprocess.run(["g++", "-O1", "-fsanitize=thread", "-pthread", "-o", str(tmp_path / "probe"), str(probe)],
+                      capture_output=True).returncode != 0:
+        pytest.skip("ThreadSanitizer not available")
+    if "ThreadSanitizer: data race" not in subprocess.run([str(tmp_path / "probe")], capture_output=True, text=True).stderr:
+        pytest.skip("ThreadSanitizer does not report races in this environment")
+    main = tmp_path / "main.cpp"
+    main.write_text(r'''
+#include <cstdio>
+#include <vector>
+extern "C" int hevce_simtrack_encode(unsigned char*, int, const unsigned char*, unsigned char*, int*, int*, int, int, int*);
+int main() {
+    const int h = 64, w = 96, cap = 256 + 2 * h * w;
+    std::vector<unsigned char> img(h * w), out(cap), rc(h * w);
+    unsigned s = 777;
+    for (int k = 0; k < h * w; k++) { s = s * 1664525u + 1013904223u; img[k] = (unsigned char)(((k % w) * 2 + (k / w) * 3 + (s >> 27)) & 255); }
+    for (int q = 0; q < 5; q += 2) {
+        int ys = h, xs = w, err = 0;
+        int n = hevce_simtrack_encode(out.data(), cap, img.data(), rc.data(), &ys, &xs, q, 0, &err);
+        printf("%d %d %d\n", q, n, err);
+    }
+}
+''')
+    exe = tmp_path / "tsan_tracks"
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", *S.variant_flags("t1"), "-I", S.CSRC,
+                    "-o", str(exe), str(main), os.path.join(S.SIM_DIR, "hevce_simtrack.cpp")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0 and "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
+    rows = [l.split() for l in out.stdout.strip().splitlines()]
+    assert len(rows) == 3 and all(int(r[1]) > 100 and int(r[2]) == 0 for r in rows)

@@ -12,8 +12,8 @@ import hevce_b200 as H  # noqa: E402
 import workloads as WL  # noqa: E402
 
 h, w, q = (int(v) for v in (sys.argv[1:4] + ["64", "64", "2"][len(sys.argv[1:4]):]))
-variants = sys.argv[4:] or ["g7", "g4", "g2", "w1"]
-gang = {"g7": 7, "g4": 4, "g2": 2, "w1": 1}
+variants = sys.argv[4:] or ["g7", "g4", "g2", "w1", "t1"]
+gang = {"g7": 7, "g4": 4, "g2": 2, "w1": 1, "t1": 1}
 K = WL.kodak_landscape()
 base = None
 for v in variants:
