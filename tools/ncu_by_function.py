@@ -11,7 +11,7 @@ import sys
 import tempfile
 
 rep = sys.argv[1]
-obj = sys.argv[2] if len(sys.argv) > 2 else "hevc-image-encoder-lite_b200/csrc/hevce_cuda.o"
+obj = sys.argv[2] if len(sys.argv) > 2 else "hevc-image-encoder-lite_b200/csrc/hevce_k_g7.o"
 core = "hevc-image-encoder-lite_b200/csrc/hevce_core.h"
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
