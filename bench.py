@@ -188,6 +188,50 @@ def gate(dg, gold, base, where):
     return n_gold
 
 
+def run_one_call(a, H, WL, torch):
+    """One process, one HEVCImageEncoderBatch call, N devices (hevce_api.c shards by CTU count, two chunk workers per device)."""
+    nd = a.one_call
+    if torch.cuda.device_count() < nd:
+        raise SystemExit(f"bench.py: --one-call {nd} needs {nd} visible GPUs")
+    H.set_devices(list(range(nd)))
+    K = WL.kodak_landscape()
+    n = a.images * nd
+    imgs = [WL.config3_image(i, K) for i in range(n)]
+    man = load_manifest("config3") if a.qpd6 == 2 else {}
+    gold = [man.get(f"{i:04d}") for i in range(n)]
+    shapes = [i.shape for i in imgs]
+    host_out = H.alloc_outputs(shapes)
+    s2, r2 = H.HEVCImageEncoderBatch(imgs, a.qpd6, outputs=host_out, copy_streams=False)      # warm-up
+    base = digests(s2, r2)
+    n_gold = gate(base, gold, None, "one-call arm, warm-up")
+    for _ in range(max(a.warmup - 1, 0)):
+        H.HEVCImageEncoderBatch(imgs, a.qpd6, outputs=host_out, copy_streams=False)
+    t = 0.0
+    with ClockSampler(0) as clk:
+        for _ in range(a.steps):
+            for d in range(nd):
+                torch.cuda.synchronize(d)
+            t0 = time.perf_counter()
+            s2, r2 = H.HEVCImageEncoderBatch(imgs, a.qpd6, outputs=host_out, copy_streams=False)
+            t += time.perf_counter() - t0
+            gate(digests(s2, r2), gold, base, "one-call arm")
+    px = n * KODAK_PIXELS
+    v = px * a.steps / t / 1e6
+    line = {
+        "metric": "Mpixel/s encoded, bit-exact bitstream, Kodak-size batch", "value": v, "unit": "Mpixel/s", "n_gpus": nd, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"configs[2]: {n} synthetic 768x512 pictures, qpd6={a.qpd6}, ONE process and ONE HEVCImageEncoderBatch call over {nd} devices",
+                   "pictures": n, "parallelism": f"library-internal: {nd} shards by CTU count, two chunk workers per device, no collective"},
+        "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": sum(i.size for i in imgs),
+                "d2h_bytes_per_step": sum(r.size for r in r2) + sum(len(x) for x in s2) + 8 * n,
+                "api": "HEVCImageEncoderBatch (host buffers); `value` is this same end-to-end figure"},
+        "gpu_launches": None, "clocks": clk.summary(),
+        "parity": {"pictures": n, "checked_against_reference_manifest": n_gold, "checked_identical_across_steps": n},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +245,9 @@ def main():
     ap.add_argument("--qpd6", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=-1, help="pictures for the cpu_baseline leg (-1 = one per host core)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--one-call", type=int, default=0, metavar="N",
+                    help="the library's own multi-GPU path: ONE process, ONE HEVCImageEncoderBatch call over N devices with N x --images "
+                         "pictures (config 3); reports the end-to-end figure only (value = e2e)")
     ap.add_argument("--single-pass", action="store_true",
                     help="long single steps (configs 4-5): ONE upload + encode + download through the session calls that "
                          "HEVCImageEncoderBatch makes; value = the encode part, e2e = the whole pass, no warm-up")
@@ -222,6 +269,8 @@ def main():
     import workloads as WL
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the encoder has no CPU path")
+    if a.one_call:
+        return run_one_call(a, H, WL, torch)
     dist = None
     if world > 1:
         import torch.distributed as dist

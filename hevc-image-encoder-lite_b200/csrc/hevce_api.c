@@ -5,9 +5,9 @@
  *   HEVCImageEncoderBatch  n independent pictures, sharded over the selected GPUs by cumulative CTU count,
  *                          no collective
  *
- * A shard (the pictures of one device) is cut into chunks of whole kernel waves; two host threads per device take
- * alternate chunks, each with its own session (stream + pinned staging), so the host<->device copies of one chunk
- * overlap the kernel of the other and the second kernel's CTAs fill the SMs the first one's tail leaves idle.
+ * A shard (the pictures of one device) is cut into chunks -- whole kernel waves for large shards, four parts for up to
+ * four waves -- and two to four host threads per device take chunks in turn, each with its own session (stream + pinned
+ * staging), so the host<->device copies of one chunk overlap the kernels of the others, whose CTAs share the SMs.
  *
  * There is no CPU encoder in this library: every picture is encoded by the sm_100a kernels; if no CUDA device can be
  * used the calls fail with HEVCE_ERR_CUDA.
@@ -26,6 +26,7 @@
 #define CHUNK_PIXELS (768LL * 1024 * 1024)    /* per-chunk bound (padded pixels) so the pinned staging stays modest */
 #define CHUNK_PICTURES 32768                  /* ... and pictures (the commit kernel's grid.y is the picture index) */
 #define WAVE_PICTURES (148 * 7)               /* pictures of one full wave of the 7-picture variant on a B200 */
+#define MAX_WORKERS 4                         /* chunk workers per device (= cached sessions per device) */
 
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;   /* device list + session pool */
 static int g_ndev = -1, g_devs[MAX_DEV];
@@ -133,7 +134,7 @@ API void hevce_release(void) {
 }
 
 typedef struct {
-    int device, first, count, status, max_dim;
+    int device, first, count, status, max_dim, variant;
     unsigned char *const *pbuffers;
     const unsigned char *const *imgs;
     unsigned char *const *rcons;
@@ -169,7 +170,7 @@ static void *chunk_worker(void *arg) {
         if (c >= sh->nchunk) break;
         a = sh->chunk_first[c];
         m = sh->chunk_first[c + 1] - a;
-        rc = hevce_session_configure(s, m, sh->ysz + a, sh->xsz + a, sh->qpd6 + a, sh->max_dim);
+        rc = hevce_session_configure(s, m, sh->ysz + a, sh->xsz + a, sh->qpd6 + a, sh->max_dim, sh->variant);
         if (!rc) rc = hevce_session_upload(s, sh->imgs + a);
         if (!rc) rc = hevce_session_encode(s);
         if (!rc) rc = hevce_session_download(s, sh->pbuffers + a, sh->rcons + a, sh->stream_len + a);
@@ -187,26 +188,41 @@ static void *chunk_worker(void *arg) {
 /* encode pictures [first, first+count) on one device */
 static void *shard_main(void *arg) {
     Shard *sh = (Shard *)arg;
-    int done = 0, cap = 16, wave_ok;
-    pthread_t helper;
+    int done = 0, cap = 16, nworkers = 2, i, same = 1;
+    pthread_t helpers[MAX_WORKERS];
     sh->status = 0;
     sh->nchunk = 0;
     sh->next_chunk = 0;
     sh->chunk_first = (int *)malloc(sizeof(int) * (size_t)(cap + 1));
     if (!sh->chunk_first) { sh->status = HEVCE_ERR_ARG; return NULL; }
     pthread_mutex_init(&sh->qlock, NULL);
+    /* the kernel variant is chosen for the whole shard: its chunks share the device */
+    sh->variant = hevce_internal_choose_variant(sh->device, sh->count, sh->ysz + sh->first, sh->xsz + sh->first, sh->max_dim);
+    for (i = 1; i < sh->count && same; i++)
+        if (sh->ysz[sh->first + i] != sh->ysz[sh->first] || sh->xsz[sh->first + i] != sh->xsz[sh->first]) same = 0;
+    if (same && sh->count >= 8 * 7 && sh->count <= MAX_WORKERS * WAVE_PICTURES &&
+        padded_pixels(sh->ysz[sh->first], sh->xsz[sh->first], sh->max_dim) * sh->count <= MAX_WORKERS * CHUNK_PIXELS) {
+        /* up to four waves of same-size pictures: four chunks (multiples of 7 pictures) on four workers whose kernels share
+           the SMs, so the upload of a chunk overlaps the kernels of the chunks before it and the downloads are staggered */
+        int per = (sh->count + MAX_WORKERS - 1) / MAX_WORKERS;
+        per = (per + 6) / 7 * 7;
+        nworkers = MAX_WORKERS;
+        while (done < sh->count) {
+            sh->chunk_first[sh->nchunk++] = sh->first + done;
+            done += per < sh->count - done ? per : sh->count - done;
+        }
+    }
     while (done < sh->count) {
-        int a = sh->first + done, m = 0, same = 1;
+        int a = sh->first + done, m = 0, same_c = 1;
         long long px = 0;
         while (done + m < sh->count && m < CHUNK_PICTURES &&
                (m == 0 || px + padded_pixels(sh->ysz[a + m], sh->xsz[a + m], sh->max_dim) <= CHUNK_PIXELS)) {
             px += padded_pixels(sh->ysz[a + m], sh->xsz[a + m], sh->max_dim);
-            if (sh->ysz[a + m] != sh->ysz[a] || sh->xsz[a + m] != sh->xsz[a]) same = 0;
+            if (sh->ysz[a + m] != sh->ysz[a] || sh->xsz[a + m] != sh->xsz[a]) same_c = 0;
             m++;
         }
         /* same-size pictures: whole waves of the 7-picture variant per chunk, so no chunk ends with a nearly empty wave */
-        wave_ok = same && m > WAVE_PICTURES && done + m < sh->count;
-        if (wave_ok) m -= m % WAVE_PICTURES;
+        if (same_c && m > WAVE_PICTURES && done + m < sh->count) m -= m % WAVE_PICTURES;
         if (sh->nchunk == cap) {
             int *p = (int *)realloc(sh->chunk_first, sizeof(int) * (size_t)(2 * cap + 1));
             if (!p) { sh->status = HEVCE_ERR_ARG; break; }
@@ -218,9 +234,12 @@ static void *shard_main(void *arg) {
     }
     sh->chunk_first[sh->nchunk] = sh->first + sh->count;
     if (!sh->status) {
-        int have_helper = sh->nchunk > 1 && pthread_create(&helper, NULL, chunk_worker, sh) == 0;
+        int nh = 0;
+        if (nworkers > sh->nchunk) nworkers = sh->nchunk;
+        for (i = 1; i < nworkers; i++)
+            if (pthread_create(&helpers[nh], NULL, chunk_worker, sh) == 0) nh++;
         chunk_worker(sh);
-        if (have_helper) pthread_join(helper, NULL);
+        for (i = 0; i < nh; i++) pthread_join(helpers[i], NULL);
     }
     pthread_mutex_destroy(&sh->qlock);
     free(sh->chunk_first);
@@ -253,7 +272,7 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
     for (i = 0; i < n; i++) total += padded_pixels(ysz[i], xsz[i], max_dim);
     /* contiguous shards with (nearly) equal padded-pixel = CTU counts */
     if (ndev > n) ndev = n;
-    hevce_internal_set_copy_threads(ndev > 1 ? (ndev >= 8 ? 2 : 8 / ndev) : 0);   /* staging copies: share the host cores between the shards */
+    hevce_internal_set_copy_threads(ndev > 1 ? (ndev >= 4 ? 1 : 2) : 4);   /* staging copies: up to 4 workers per shard share the host cores */
     for (k = 0, i = 0; k < ndev; k++) {
         int first = i;
         long long want = total * (k + 1) / ndev;

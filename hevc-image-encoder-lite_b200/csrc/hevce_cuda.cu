@@ -265,7 +265,46 @@ static int stage_reserve(hevce_session* s, size_t need) {
     return 0;
 }
 
-extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, const int* xsz, const int* qpd6, int max_dim) {
+// The variant (index into the variant table) that finishes these pictures soonest on one device by the
+// longest-processing-time estimate: makespan over the SMs in CTUs x the variant's measured time per CTU.
+static int choose_variant(int sms, const std::vector<Job>& jobs, const std::vector<int>& order) {
+    int best = g_forced_variant;
+    if (best >= 0) return best;
+    double best_t = 0;
+    for (int v = 0; v < NVARIANT; v++) {
+        const double t = (double)build_gangs(jobs, order, g_variants[v].vi.gang, sms, nullptr) * g_variants[v].cost;
+        if (best < 0 || t < best_t) { best = v; best_t = t; }
+    }
+    return best;
+}
+
+static void size_order(const std::vector<Job>& jobs, std::vector<int>& order) {   // largest pictures first, same sizes adjacent
+    order.resize(jobs.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const Job &x = jobs[a], &y = jobs[b];
+        const long long ax = (long long)x.H * x.W, ay = (long long)y.H * y.W;
+        if (ax != ay) return ax > ay;
+        if (x.H != y.H) return x.H > y.H;
+        return false;
+    });
+}
+
+// For a caller that cuts one device's pictures into several chunks that run at the same time (hevce_api.c): the
+// variant is chosen for ALL of them together, then forced on every chunk's session.  returns a variant index or < 0.
+extern "C" int hevce_internal_choose_variant(int device, int n, const int* ysz, const int* xsz, int max_dim) {
+    if (device_prepare(device) || n <= 0) return -1;
+    std::vector<Job> jobs((size_t)n);
+    for (int i = 0; i < n; i++) {
+        jobs[i].H = (std::min(ysz[i], max_dim) + CTU - 1) / CTU * CTU;
+        jobs[i].W = (std::min(xsz[i], max_dim) + CTU - 1) / CTU * CTU;
+    }
+    std::vector<int> order;
+    size_order(jobs, order);
+    return choose_variant(g_dev[device].sms, jobs, order);
+}
+
+extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, const int* xsz, const int* qpd6, int max_dim, int variant) {
     if (!s || n < 0 || n > 65535 || (n > 0 && (!ysz || !xsz || !qpd6))) return HEVCE_ERR_ARG;   // grid.y of the commit kernel = picture index
     int rc = device_prepare(s->device);
     if (rc) return rc;
@@ -298,24 +337,9 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     if (n == 0) return 0;
     // work units: gangs of same-size pictures, largest pictures first; the variant (pictures per CTA) that finishes the
     // batch soonest by the longest-processing-time estimate: makespan in CTUs x the variant's time per CTU
-    s->order.resize(n);
-    std::iota(s->order.begin(), s->order.end(), 0);
-    std::stable_sort(s->order.begin(), s->order.end(), [&](int a, int b) {
-        const Job &x = s->jobs[a], &y = s->jobs[b];
-        const long long ax = (long long)x.H * x.W, ay = (long long)y.H * y.W;
-        if (ax != ay) return ax > ay;
-        if (x.H != y.H) return x.H > y.H;
-        return false;
-    });
+    size_order(s->jobs, s->order);
     const DeviceInfo& di = g_dev[s->device];
-    int best = g_forced_variant;
-    if (best < 0) {
-        double best_t = 0;
-        for (int v = 0; v < NVARIANT; v++) {
-            const double t = (double)build_gangs(s->jobs, s->order, g_variants[v].vi.gang, di.sms, nullptr) * g_variants[v].cost;
-            if (best < 0 || t < best_t) { best = v; best_t = t; }
-        }
-    }
+    const int best = (variant >= 0 && variant < NVARIANT) ? variant : choose_variant(di.sms, s->jobs, s->order);
     s->variant = best;
     const int GANGV = g_variants[best].vi.gang;
     std::vector<int> gangs;
@@ -374,7 +398,7 @@ extern "C" hevce_session* hevce_session_create_empty(int device) {
 
 extern "C" hevce_session* hevce_session_create(int device, int n, const int* ysz, const int* xsz, const int* qpd6) {
     hevce_session* s = hevce_session_create_empty(device);
-    if (s && hevce_session_configure(s, n, ysz, xsz, qpd6, hevce_internal_max_dim())) { hevce_session_destroy(s); return nullptr; }
+    if (s && hevce_session_configure(s, n, ysz, xsz, qpd6, hevce_internal_max_dim(), -1)) { hevce_session_destroy(s); return nullptr; }
     return s;
 }
 

@@ -11,7 +11,8 @@ int hevce_internal_get_device(void);          /* the calling thread's current CU
 void hevce_internal_set_device(int device);   /* no-op for device < 0 */
 void hevce_internal_set_copy_threads(int n);  /* host threads used for staging copies by each session */
 hevce_session *hevce_session_create_empty(int device);
-int hevce_session_configure(hevce_session *s, int n, const int *ysz, const int *xsz, const int *qpd6, int max_dim);
+int hevce_internal_choose_variant(int device, int n, const int *ysz, const int *xsz, int max_dim);   /* variant index or < 0 */
+int hevce_session_configure(hevce_session *s, int n, const int *ysz, const int *xsz, const int *qpd6, int max_dim, int variant);   /* variant < 0: choose */
 void hevce_session_padded_size(const hevce_session *s, int i, int *H, int *W);
 #ifdef __cplusplus
 }
