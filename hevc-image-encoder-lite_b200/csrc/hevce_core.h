@@ -49,6 +49,22 @@
 #ifndef HEVCE_OPT_BINSEL
 #define HEVCE_OPT_BINSEL 1
 #endif
+// Consecutive bypass strings of one syntax element coded by ONE put_bypass call (the reference issues one call per bit of
+// the last-position suffixes and two per escape level, HEVCe.c:1076-1086, 1154-1169).  Exact for everything observable:
+// bypass coding is linear (low = low * 2^n + range * bits) and a byte leaves the window whenever fewer than 12 bits of
+// headroom remain, whatever the grouping, so the bytes, their count (the rate, emulation prevention included) and
+// {range, nbits} are the same; only WHEN a carry reaches the pending byte can differ (it may still sit in `low` where the
+// call-for-call coder has already added it).  Trial and commit coders use the same grouping, so their states still have
+// to agree exactly.  tests/test_stages.py: random sequences in both groupings give identical byte streams; the
+// call-for-call build equals the reference's putCoef state field by field; measured -5 % kernel time (g7).
+#ifndef HEVCE_OPT_BYPMERGE
+#define HEVCE_OPT_BYPMERGE 1
+#endif
+// Trial coder: the common byte release (exactly one pending byte, its value above 3, so no emulation-prevention byte and
+// no zero run can be involved) as a short straight path in front of the general state machine.
+#ifndef HEVCE_OPT_FASTREL
+#define HEVCE_OPT_FASTREL 0
+#endif
 // ---- kernel variant (one translation unit per variant, see hevce_variant.cu): pictures per CTA, threads per picture,
 // trial lanes per warp and the pool plan.  GANG x NT threads run in lock-step phases; WIDE = one picture owns the CTA
 // and most of the SM's shared memory (all 35 candidates of a 16x16 / 32x32 step in one round).
@@ -295,6 +311,18 @@ struct BacT {
         const int lead = c.low >> (24 - c.nbits);
         c.nbits += 8;
         c.low &= (int)(0xFFFFFFFFu >> c.nbits);
+#if HEVCE_OPT_FASTREL
+        if (!EMIT) {
+            const int b = (c.held + (lead >> 8)) & 0xff;
+            if (lead != 0xff && (c.nbytes == 0 || (c.nbytes == 1 && b > 3))) {
+                c.n += c.nbytes;
+                c.z = c.nbytes ? 0 : c.z;
+                c.held = c.nbytes ? (lead & 0xff) : lead;
+                c.nbytes = 1;
+                return;
+            }
+        }
+#endif
         if (EMIT || !HEVCE_OPT_FLUSH) {
             if (lead == 0xff) c.nbytes++;
             else if (c.nbytes > 0) {
@@ -778,8 +806,15 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
         if (gx < gmax) b.put_bin(tbl, 0, cx[bx + (gx >> sh)]);
         for (int i = 0; i < gy; i++) b.put_bin(tbl, 1, cx[by + (i >> sh)]);
         if (gy < gmax) b.put_bin(tbl, 0, cx[by + (gy >> sh)]);
+#if HEVCE_OPT_BYPMERGE
+        {   // both suffixes (<= 3 bits each) as one string
+            const int nx = gx > 3 ? (gx - 2) >> 1 : 0, ny = gy > 3 ? (gy - 2) >> 1 : 0;
+            if (nx + ny) b.put_bypass(((gx > 3 ? tx - tb->gmin[gx] : 0) << ny) | (gy > 3 ? ty - tb->gmin[gy] : 0), nx + ny);
+        }
+#else
         if (gx > 3) { tx -= tb->gmin[gx]; for (int i = ((gx - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((tx >> i) & 1, 1); }   // one bin per call,
         if (gy > 3) { ty -= tb->gmin[gy]; for (int i = ((gy - 2) >> 1) - 1; i >= 0; i--) b.put_bypass((ty >> i) & 1, 1); }   // as HEVCe.c:1076-1086
+#endif
     }
     // ---- sig_coeff_flags (HEVCe.c:1219-1222, context HEVCe.c:1092-1122)
     {
@@ -820,7 +855,19 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
             g2 &= 1;
             if (c1 == 0) { b.put_bin(tbl, g2, cx[CX_ABS + set]); esc |= g2; }
         }
+#if HEVCE_OPT_BYPMERGE >= 2
+        // everything that follows in this group is bypass-coded (signs, then the remaining levels): one bit string,
+        // handed to the coder in pieces of at most 30 bits
+        unsigned acc = (unsigned)signs;
+        int accn = nz;
+        auto append = [&](unsigned bits, int n) {
+            if (accn + n > 30) { b.put_bypass((int)acc, accn); acc = 0; accn = 0; }
+            acc = (acc << n) | bits;
+            accn += n;
+        };
+#else
         b.put_bypass(signs, nz);
+#endif
         // ---- coeff_abs_level_remaining (HEVCe.c:1254-1266, 1154-1169)
         if (esc) {
             int base = 3, rp = 0, j = 0;
@@ -834,15 +881,32 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
                 if (v >= 0) {
                     if (v < (3 << rp)) {
                         const int n = v >> rp;
+#if HEVCE_OPT_BYPMERGE >= 2
+                        append((unsigned)((((1 << (n + 1)) - 2) << rp) | (v & ((1 << rp) - 1))), n + 1 + rp);
+#elif HEVCE_OPT_BYPMERGE
+                        b.put_bypass((((1 << (n + 1)) - 2) << rp) | (v & ((1 << rp) - 1)), n + 1 + rp);   // <= 8 bits: one chunk
+#else
                         b.put_bypass((1 << (n + 1)) - 2, n + 1);
                         b.put_bypass(v & ((1 << rp) - 1), rp);
+#endif
                     } else {
                         int n = rp;
                         v -= 3 << rp;
                         for (; v >= (1 << n); n++) v -= 1 << n;
                         const int pre = 4 + n - rp;
-                        b.put_bypass((1 << pre) - 2, pre);
-                        b.put_bypass(v, n);
+#if HEVCE_OPT_BYPMERGE >= 2
+                        if (pre + n <= 30) append((unsigned)((((1 << pre) - 2) << n) | v), pre + n);
+                        else { append((unsigned)((1 << pre) - 2), pre); append((unsigned)v, n); }
+#else
+#if HEVCE_OPT_BYPMERGE
+                        if (pre + n <= 30) b.put_bypass((((1 << pre) - 2) << n) | v, pre + n);
+                        else
+#endif
+                        {
+                            b.put_bypass((1 << pre) - 2, pre);
+                            b.put_bypass(v, n);
+                        }
+#endif
                     }
                     if (a > (3 << rp)) rp = imin(rp + 1, 4);
                 }
@@ -850,6 +914,9 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
                 j++;
             }
         }
+#if HEVCE_OPT_BYPMERGE >= 2
+        b.put_bypass((int)acc, accn);
+#endif
     }
 
 }
@@ -978,8 +1045,12 @@ HEVCE_HD HEVCE_NOINLINE void code_cu(BAC& bio, int pic, int cx_off, int cx_s4, c
         }
         for (int i = 0; i < n; i++) {
             if (hit[i] >= 0) {
+#if HEVCE_OPT_BYPMERGE
+                b.put_bypass(hit[i] > 0 ? 2 + (hit[i] - 1) : 0, hit[i] > 0 ? 2 : 1);   // mpm_idx: 0 / 10 / 11
+#else
                 b.put_bypass(hit[i] > 0, 1);
                 if (hit[i] > 0) b.put_bypass(hit[i] - 1, 1);
+#endif
             } else {
                 int r = d.pm[i];
                 const int hi = imax(mp[i][0], imax(mp[i][1], mp[i][2])), lo = imin(mp[i][0], imin(mp[i][1], mp[i][2]));

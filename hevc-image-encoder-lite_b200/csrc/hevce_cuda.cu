@@ -132,7 +132,7 @@ void variants_init() {
     std::call_once(g_variants_once, [] {
         fill_tables(g_host_tables);
         // relative per-CTU latency of a gang (all SMs busy with the same variant), measured on B200 -- profiles/r2_notes.md
-        static const double kCost[NVARIANT] = {1.00, 0.79, 0.68, 0.59, 0.54};   // 9.13 / 7.23 / 6.21 / 5.42 / 4.97 ms per CTU, 148 gangs of 64x64 pictures, qpd6=2
+        static const double kCost[NVARIANT] = {1.00, 0.74, 0.63, 0.54, 0.52};   // 8.63 / 6.38 / 5.42 / 4.65 / 4.46 ms per CTU, 148 gangs of 64x64 pictures, qpd6=2
         for (int v = 0; v < NVARIANT; v++) { g_variants[v].info(&g_variants[v].vi); g_variants[v].cost = kCost[v]; }
         if (const char* env = getenv("HEVCE_VARIANT"))
             for (int v = 0; v < NVARIANT; v++) if (!strcmp(env, g_variants[v].name)) g_forced_variant = v;

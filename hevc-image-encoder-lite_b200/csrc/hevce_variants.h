@@ -14,10 +14,10 @@ typedef struct hevce_variant_info {
 /* tag, pictures per CTA, threads per picture, lanes per warp, wide pool */
 #define HEVCE_VARIANT_LIST(X) \
     X(g7, 7, 128, 32, 0)      \
-    X(g4, 4, 224, 16, 0)      \
-    X(g2, 2, 448, 8, 0)       \
-    X(w1, 1, 896, 4, 1)       \
-    X(t1, 1, 896, 6, 0)
+    X(g4, 4, 224, 24, 0)      \
+    X(g2, 2, 448, 16, 0)       \
+    X(w1, 1, 896, 8, 1)       \
+    X(t1, 1, 896, 12, 0)
 
 #ifdef __cplusplus
 extern "C" {

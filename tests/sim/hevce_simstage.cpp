@@ -103,3 +103,46 @@ extern "C" int hevce_stage_residual(int T, int mode, int q, const int* lev, int*
     state[0] = b.c.range; state[1] = b.c.low; state[2] = b.c.nbits; state[3] = b.c.nbytes; state[4] = b.c.held; state[5] = b.c.z; state[6] = b.c.n;
     return coder_len(b.c) - len0;
 }
+
+// Bypass grouping: the same random sequence of context bins and bypass strings through the byte-writing coder, once with
+// every bypass string in ONE put_bypass call and once cut into random pieces (one call each, down to one bit per call as
+// the reference does for the last-position suffixes).  Returns 0 when both byte streams (incl. emulation prevention and
+// the final flush) are identical, else the 1-based position of the first difference; *len receives the stream length.
+extern "C" int hevce_stage_bypass_grouping(unsigned seed, int nitems, int* len) {
+    const Tables& tb = *tables();
+    auto rnd = [&seed]() { seed = seed * 1664525u + 1013904223u; return seed >> 8; };
+    struct Item { int ctx, bin, bits, n; };
+    std::vector<Item> items((size_t)nitems);
+    for (auto& it : items) {
+        if (rnd() % 3 == 0) { it.ctx = (int)(rnd() % NCTX); it.bin = (int)(rnd() & 1); it.n = 0; it.bits = 0; }
+        else { it.ctx = -1; it.n = 1 + (int)(rnd() % 30); it.bits = (int)(rnd() ^ (rnd() << 12)) & ((1 << it.n) - 1); it.bin = 0; }
+        if (rnd() % 17 == 0 && it.ctx < 0) it.bits = 0;                                  // zero runs: emulation prevention
+    }
+    std::vector<u8> out[2];
+    for (int pass = 0; pass < 2; pass++) {
+        u8 ctx[4 * CTXW];
+        for (int i = 0; i < 4 * CTXW; i++) ctx[i] = ctx_init_value(tb.ctx_iv[i], 2);
+        out[pass].assign((size_t)nitems * 8 + 64, 0);
+        BacCommit b;
+        coder_reset(b.c);
+        b.out = out[pass].data(); b.cap = (int)out[pass].size();
+        unsigned s2 = seed ^ 0x9e3779b9u;
+        auto rnd2 = [&s2]() { s2 = s2 * 1664525u + 1013904223u; return s2 >> 8; };
+        for (const auto& it : items) {
+            if (it.ctx >= 0) { b.put_bin(tb, it.bin, ctx[it.ctx]); continue; }
+            if (pass == 0) { b.put_bypass(it.bits, it.n); continue; }
+            for (int left = it.n; left > 0;) {                                           // MSB-first pieces
+                const int k = 1 + (int)(rnd2() % (unsigned)imin(left, 5));
+                b.put_bypass((it.bits >> (left - k)) & ((1 << k) - 1), k);
+                left -= k;
+            }
+        }
+        b.put_terminate(1);
+        b.finish();
+        out[pass].resize((size_t)b.c.n);
+    }
+    *len = (int)out[0].size();
+    if (out[0].size() != out[1].size()) return 1 + (int)imin((int)out[0].size(), (int)out[1].size());
+    for (size_t i = 0; i < out[0].size(); i++) if (out[0][i] != out[1][i]) return 1 + (int)i;
+    return 0;
+}

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "hevc-image-encoder-lite_b200", "csrc")
-OUT = os.path.join(ROOT, "hevc-image-encoder-lite_b200", "ab")
+OUT = os.environ.get("HEVCE_AB_DIR") or os.path.join(ROOT, "hevc-image-encoder-lite_b200", "ab")
 ARCH = "-gencode arch=compute_100a,code=sm_100a"
 FLAGS = f"{ARCH} -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden"
 
