@@ -170,6 +170,7 @@ struct Tables {
     u8 sigp4[16];          // sig_coeff ctx for 4x4 TUs                     (HEVCe.c:1093)
     u8 grp[32];            // last-position group index                     (HEVCe.c:1047)
     u8 gmin[12];           // first position of a group                     (HEVCe.c:1048)
+    int rate32[32];        // RDOQ rate estimate of levels 0..31                (HEVCe.c:526-535)
 };
 
 inline void fill_tables(Tables& t) {
@@ -244,6 +245,8 @@ inline void fill_tables(Tables& t) {
     for (int i = 0; i < 16; i++) t.sigp4[i] = P4[i];
     for (int i = 0; i < 32; i++) t.grp[i] = (u8)(i < 4 ? i : i < 6 ? 4 : i < 8 ? 5 : i < 12 ? 6 : i < 16 ? 7 : i < 24 ? 8 : 9);
     for (int i = 0; i < 12; i++) t.gmin[i] = GMIN[i];
+    for (int l = 0; l < 32; l++)
+        t.rate32[l] = l == 0 ? 0 : l == 1 ? 70000 : l == 2 ? 90000 : l == 3 ? 92000 : l == 4 ? 157536 : l == 5 ? 190304 : 92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15);
 }
 
 // context initialisation for QP = 6*qpd6+4 (HEVCe.c:727-735)
@@ -529,7 +532,6 @@ struct Shared {
     int q;                              // qpd6
     int cand_sse[NCAND], cand_bits[NCAND];   // cand_bits: trial bits; RD cost once a one-TU / four-TU lane has finished
     unsigned cgnz[NCAND][4];            // non-zero-group bitmaps: one-TU: [0],[1] = low/high word; else [tu]
-    int rate6[6];                       // RDOQ: weighted rate of levels 0..5
     int nxn_pm[4], nxn_cost;
     unsigned nxn_nz[4];
     int part_sse[CTU];
@@ -855,19 +857,7 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
             g2 &= 1;
             if (c1 == 0) { b.put_bin(tbl, g2, cx[CX_ABS + set]); esc |= g2; }
         }
-#if HEVCE_OPT_BYPMERGE >= 2
-        // everything that follows in this group is bypass-coded (signs, then the remaining levels): one bit string,
-        // handed to the coder in pieces of at most 30 bits
-        unsigned acc = (unsigned)signs;
-        int accn = nz;
-        auto append = [&](unsigned bits, int n) {
-            if (accn + n > 30) { b.put_bypass((int)acc, accn); acc = 0; accn = 0; }
-            acc = (acc << n) | bits;
-            accn += n;
-        };
-#else
         b.put_bypass(signs, nz);
-#endif
         // ---- coeff_abs_level_remaining (HEVCe.c:1254-1266, 1154-1169)
         if (esc) {
             int base = 3, rp = 0, j = 0;
@@ -881,9 +871,7 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
                 if (v >= 0) {
                     if (v < (3 << rp)) {
                         const int n = v >> rp;
-#if HEVCE_OPT_BYPMERGE >= 2
-                        append((unsigned)((((1 << (n + 1)) - 2) << rp) | (v & ((1 << rp) - 1))), n + 1 + rp);
-#elif HEVCE_OPT_BYPMERGE
+#if HEVCE_OPT_BYPMERGE
                         b.put_bypass((((1 << (n + 1)) - 2) << rp) | (v & ((1 << rp) - 1)), n + 1 + rp);   // <= 8 bits: one chunk
 #else
                         b.put_bypass((1 << (n + 1)) - 2, n + 1);
@@ -894,10 +882,6 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
                         v -= 3 << rp;
                         for (; v >= (1 << n); n++) v -= 1 << n;
                         const int pre = 4 + n - rp;
-#if HEVCE_OPT_BYPMERGE >= 2
-                        if (pre + n <= 30) append((unsigned)((((1 << pre) - 2) << n) | v), pre + n);
-                        else { append((unsigned)((1 << pre) - 2), pre); append((unsigned)v, n); }
-#else
 #if HEVCE_OPT_BYPMERGE
                         if (pre + n <= 30) b.put_bypass((((1 << pre) - 2) << n) | v, pre + n);
                         else
@@ -906,7 +890,6 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
                             b.put_bypass((1 << pre) - 2, pre);
                             b.put_bypass(v, n);
                         }
-#endif
                     }
                     if (a > (3 << rp)) rp = imin(rp + 1, 4);
                 }
@@ -914,9 +897,6 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
                 j++;
             }
         }
-#if HEVCE_OPT_BYPMERGE >= 2
-        b.put_bypass((int)acc, accn);
-#endif
     }
 
 }
@@ -1272,6 +1252,7 @@ HEVCE_HD inline void phase_b_item(Shared& sm, const Shared& pm, const Grp& g, in
     }
     const int dsh = 10 - LG, sh = 21 - LG + q, add = 1 << sh >> 1, thr = 9 << sh >> 2;
     const int wd = rk.wd, wb = rk.wb;
+    const int* rate32 = my_tb().rate32;
     int* ps = (int*)(sm.pool + g.psum) + c * (T * T / 4) + y * (T / 4);
 #pragma unroll 1
     for (int gx = 0; gx < T / 4; gx++) {
@@ -1289,7 +1270,7 @@ HEVCE_HD inline void phase_b_item(Shared& sm, const Shared& pm, const Grp& g, in
                     const int l = lvl - t;
                     const int d1 = iabs(dl - (l << sh)) >> dsh;
                     const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
-                    const int wr = l < 6 ? pm.rate6[imax(l, 0)] : wb * (92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15));   // HEVCe.c:526-535
+                    const int wr = wb * (l < 32 ? rate32[imax(l, 0)] : 92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15));   // HEVCe.c:526-535
                     const int cost = wd * d + wr;
                     if (l >= 0 && cost < best) { best = cost; pick = l; }
                 }
@@ -1945,10 +1926,6 @@ HEVCE_HD inline void encode_picture(const Job& job, const Scratch* scs) {
     }
     PIC_FOR(i, 81) { sm.msz[i] = CTU; sm.mpm[i] = 1; }
     PIC_FOR(i, W / 4) sc.msz_line[i] = CTU;
-    PIC_FOR(lvl, 6) {
-        const RdK rk = rd_consts(q);
-        sm.rate6[lvl] = rk.wb * (lvl == 0 ? 0 : lvl == 1 ? 70000 : lvl == 2 ? 90000 : lvl == 3 ? 92000 : lvl == 4 ? 157536 : 190304);   // HEVCe.c:527
-    }
     PIC_FOR(t, NTRACK) blk_sm(HEVCE_SLOT * NTRACK + t).sc = scs[t];
     PIC_FOR(one, 1) {
         coder_reset(sm.live);

@@ -51,8 +51,6 @@ extern "C" int hevce_stage_pixel(int T, int mode, int q, const unsigned char* wi
     g_sim_sms = sm; g_sim_tb = tables(); g_sim_trk = 0; g_sim_member = 0;
     memcpy(sm->win, win, sizeof(sm->win));
     memcpy(sm->orig, orig, sizeof(sm->orig));
-    const RdK rk = rd_consts(q);
-    for (int l = 0; l < 6; l++) sm->rate6[l] = rk.wb * (l == 0 ? 0 : l == 1 ? 70000 : l == 2 ? 90000 : l == 3 ? 92000 : l == 4 ? 157536 : 190304);
     std::vector<s16> glev((size_t)NCAND * LEV_STRIDE + 16);
     std::vector<u8> grec((size_t)NREC * CTU * CTU);
     Scratch sc;
