@@ -86,6 +86,9 @@
 #ifndef HEVCE_OPT_TRK_C
 #define HEVCE_OPT_TRK_C HEVCE_OPT_NT
 #endif
+#ifndef HEVCE_OPT_CLUSTER  // 2: the tracks of a picture on a thread-block cluster of two CTAs (two SMs): rank 0 = track 0 with all
+#define HEVCE_OPT_CLUSTER 0 //   its threads, rank 1 = tracks 1 and 2 with half each; state crosses through distributed shared memory
+#endif
 #ifndef HEVCE_OPT_LPW_P    // trial lanes per warp on the two parent tracks
 #define HEVCE_OPT_LPW_P HEVCE_OPT_LPW
 #endif
@@ -112,14 +115,16 @@ constexpr bool WIDE = HEVCE_OPT_WIDE != 0;
 // 8x8 nodes plus every decision / adoption, track 1 = the candidates of the 16x16 nodes, track 2 = those of the 32x32 node.
 constexpr bool TRACKS = HEVCE_OPT_TRACKS != 0;
 constexpr int NTRACK = TRACKS ? 3 : 1;
-constexpr int TRK_C = TRACKS ? HEVCE_OPT_TRK_C : NT;      // threads of track 0
-constexpr int TRK_P = TRACKS ? (NT - TRK_C) / 2 : 0;      // threads of track 1 and of track 2
+constexpr bool CLUSTER = HEVCE_OPT_CLUSTER != 0;          // tracks on the two CTAs of a cluster (NT threads each)
+constexpr int TRK_C = CLUSTER ? NT : TRACKS ? HEVCE_OPT_TRK_C : NT;      // threads of track 0
+constexpr int TRK_P = CLUSTER ? NT / 2 : TRACKS ? (NT - TRK_C) / 2 : 0;  // threads of track 1 and of track 2
 constexpr int LPW_P = HEVCE_OPT_LPW_P;
 constexpr int NTA = (TRK_C / 2) / 32 * 32, NTB = TRK_C - NTA;   // the two thread teams of track 0 on 8x8 nodes: [0, NTA) and [NTA, TRK_C)
 static_assert(NT % 32 == 0 && NTA >= 32 && LPW >= 1 && LPW <= 32 && LPW_P >= 1 && LPW_P <= 32, "bad kernel variant");
-static_assert(!TRACKS || (GANG == 1 && TRK_C % 64 == 0 && TRK_P % 32 == 0 && TRK_P >= 96 && TRK_C + 2 * TRK_P == NT), "bad track split");
+static_assert(!TRACKS || (GANG == 1 && TRK_C % 64 == 0 && TRK_P % 32 == 0 && TRK_P >= 96 && TRK_C + 2 * TRK_P == (CLUSTER ? 2 * NT : NT)), "bad track split");
+static_assert(!CLUSTER || TRACKS, "the cluster variant is a track variant");
 HEVCE_HD inline int trk_of_tid(int tid) { return (!TRACKS || tid < TRK_C) ? 0 : tid < TRK_C + TRK_P ? 1 : 2; }
-HEVCE_HD inline int trk_t0(int t) { return t == 0 ? 0 : t == 1 ? TRK_C : TRK_C + TRK_P; }
+HEVCE_HD inline int trk_t0(int t) { return CLUSTER ? (t == 2 ? TRK_P : 0) : t == 0 ? 0 : t == 1 ? TRK_C : TRK_C + TRK_P; }   // first thread of the track in its CTA
 HEVCE_HD inline int trk_size(int t) { return t == 0 ? TRK_C : TRK_P; }
 HEVCE_HD inline int trk_lpw(int t) { return t == 0 ? LPW : LPW_P; }
 template <int S> struct TrackOf { static constexpr int value = !TRACKS ? 0 : S == 8 ? 0 : S == 16 ? 1 : 2; };
@@ -515,29 +520,36 @@ constexpr int POOL_BYTES = TRACKS ? 53248 : WIDE ? 189440 : 18624;
 constexpr int AUX_CODER = POOL_BYTES - 1984;       // pool tail: trial-coder results (free whenever they are used)
 
 struct Shared {
+    // ---- the track's own working state
     alignas(16) u8 pool[POOL_BYTES];    // per-node carve-up: work blocks, predictions, borders (see Plan<S>)
     u32 lane_ctx[CTXW * NLANE];         // lane-private context sets, word-interleaved
+    Scratch sc;                         // this track's global scratch (trial lanes may run on another picture's threads)
+    int cand_sse[NCAND], cand_bits[NCAND];   // cand_bits: trial bits; RD cost once a one-TU / four-TU lane has finished
+    unsigned cgnz[NCAND][4];            // non-zero-group bitmaps: one-TU: [0],[1] = low/high word; else [tu]
+    // ---- the picture's state: owned by track 0; the cluster variant pushes [ctx0, mirror_end) into the parent tracks' blocks
     alignas(16) u8 ctx0[4 * CTXW];      // freshly initialised contexts for this picture's qpd6
     alignas(16) u8 live_ctx[4 * CTXW];
     alignas(16) u8 snap_ctx[3][4 * CTXW];
-    alignas(16) u8 nxn_ctx[4 * CTXW];
-    alignas(16) s16 nxn_lev[4][16];
     u8 orig[CTU * CTU];
     u8 win[(CTU + 1) * WP];
     u8 msz[81], mpm[81];                // [1+uy][1+ux], 4x4 units; row 0 / col 0 = neighbours
     u8 kind[16];                        // per 8x8 unit: 0 one TU, 1 four TUs, 2 NxN
-    Coder live, snap[3], nxn_coder;
-    s16* ctu_lev;                       // level store of the current CTU (Job::levs + ctu*1024)
-    Scratch sc;                         // this picture slot's global scratch (trial lanes may run on another picture's threads)
+    Coder live, snap[3];
     int q;                              // qpd6
-    int cand_sse[NCAND], cand_bits[NCAND];   // cand_bits: trial bits; RD cost once a one-TU / four-TU lane has finished
-    unsigned cgnz[NCAND][4];            // non-zero-group bitmaps: one-TU: [0],[1] = low/high word; else [tu]
+    int mirror_end;                     // (marker) end of the mirrored range
+    // ---- track 0 only
+    alignas(16) u8 nxn_ctx[4 * CTXW];
+    alignas(16) s16 nxn_lev[4][16];
+    Coder nxn_coder;
+    s16* ctu_lev;                       // level store of the current CTU (Job::levs + ctu*1024)
+    Scratch sc_of[3];                   // the scratch of every track (adoption reads the winner from the evaluating track's)
     int nxn_pm[4], nxn_cost;
     unsigned nxn_nz[4];
     int part_sse[CTU];
     int win_item;                       // decision of the current node: -1 keep split, 0..NREC-1 candidate, NCAND = NxN
     int stream_pos;
     int error;
+    unsigned rdv_seq[3];                // cluster variant: rendezvous sequence numbers written by the partner track
     long long prof_last;
 };
 
@@ -552,14 +564,44 @@ struct GangCtl { int nlive; int next; };
 // original, maps, live / snapshot coder state ...) are those of the picture's track-0 block (pic_sm()).  Non-inlined
 // functions fetch the blocks through these accessors instead of taking reference parameters: the compiler then knows
 // the address space and emits LDS/STS instead of generic loads.  The constant tables exist once per CTA, behind the blocks.
+// Cluster variant: a CTA holds the blocks of ITS tracks only (rank 0: track 0; rank 1: tracks 1 and 2); every track works on
+// its own block, whose picture-level fields are a mirror that track 0 pushes through distributed shared memory before it
+// releases the track (push_picture_state); track 0 fetches a parent track's results the same way (decide_adopt).
+#if defined(__CUDACC__)
+constexpr int NBLOCK = CLUSTER ? 2 : GANG * NTRACK;           // blocks in one CTA's shared memory
+HEVCE_HD inline int local_block(int slot, int trk) { return CLUSTER ? (trk == 2 ? 1 : 0) : slot * NTRACK + trk; }
+#else   // the simulators keep all tracks' blocks of a picture side by side, also for the cluster variant
 constexpr int NBLOCK = GANG * NTRACK;
+HEVCE_HD inline int local_block(int slot, int trk) { return slot * NTRACK + trk; }
+#endif
+// the block that holds the picture-level state a thread of (slot, trk) works with
+HEVCE_HD inline int picture_block(int slot, int trk) { return CLUSTER ? local_block(slot, trk) : local_block(slot, 0); }
 #if defined(__CUDA_ARCH__)
 extern __shared__ __align__(16) unsigned char hevce_smem[];
-#define HEVCE_SLOT ((int)(threadIdx.x / NT))
-#define HEVCE_PTID ((int)(threadIdx.x % NT))                       /* thread of the picture */
-#define HEVCE_TRK trk_of_tid(HEVCE_PTID)
+__device__ __forceinline__ int cluster_rank() { unsigned r = 0; if (CLUSTER) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+#define HEVCE_SLOT (CLUSTER ? 0 : (int)(threadIdx.x / NT))
+#define HEVCE_PTID ((int)(threadIdx.x % NT))                       /* thread of the picture (cluster: of the CTA) */
+#define HEVCE_TRK (CLUSTER ? (cluster_rank() == 0 ? 0 : ((int)threadIdx.x < TRK_P ? 1 : 2)) : trk_of_tid(HEVCE_PTID))
 #define HEVCE_TID (HEVCE_PTID - trk_t0(HEVCE_TRK))                 /* thread of the track   */
 __device__ __forceinline__ Shared& blk_sm(int b) { return reinterpret_cast<Shared*>(hevce_smem)[b]; }
+// track t's block as seen from another CTA of the cluster (generic pointer into that CTA's shared memory)
+__device__ __forceinline__ Shared* remote_blk(int t) {
+    Shared* p = &blk_sm(local_block(0, t));
+#if HEVCE_OPT_CLUSTER
+    unsigned long long in = (unsigned long long)p, out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(in), "r"(t == 0 ? 0 : 1));
+    p = (Shared*)out;
+#endif
+    return p;
+}
+__device__ __forceinline__ void rdv_signal(unsigned* flag, unsigned v) {   // release everything this track wrote, then raise the partner's flag
+    asm volatile("fence.acq_rel.cluster;\n\tst.release.cluster.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+}
+__device__ __forceinline__ void rdv_wait(const unsigned* flag, unsigned v) {
+    unsigned x;
+    do { asm volatile("ld.acquire.cluster.u32 %0, [%1];" : "=r"(x) : "l"(flag) : "memory"); } while (x != v);
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");   // also drops this SM's L1 lines of the partner's global scratch
+}
 __device__ __forceinline__ Tables& my_tb() { return *reinterpret_cast<Tables*>(hevce_smem + NBLOCK * sizeof(Shared)); }
 __device__ __forceinline__ GangCtl& gang_ctl() { return *reinterpret_cast<GangCtl*>(hevce_smem + NBLOCK * sizeof(Shared) + sizeof(Tables)); }
 __device__ __forceinline__ int gang_live() { return GANG == 1 ? 1 : gang_ctl().nlive; }
@@ -569,6 +611,8 @@ __device__ __forceinline__ int gang_live() { return GANG == 1 ? 1 : gang_ctl().n
 #define HEVCE_TRK 0
 #define HEVCE_TID 0
 inline Shared& blk_sm(int) { return *static_cast<Shared*>(nullptr); }   // host pass of nvcc: declared, never executed
+inline Shared* remote_blk(int) { return nullptr; }
+inline int cluster_rank() { return 0; }
 inline Tables& my_tb() { return *static_cast<Tables*>(nullptr); }
 inline GangCtl& gang_ctl() { return *static_cast<GangCtl*>(nullptr); }
 inline int gang_live() { return GANG; }
@@ -585,12 +629,13 @@ void sim_barrier(int id, int parties);
 #define HEVCE_SLOT g_sim_member
 #define HEVCE_TRK g_sim_trk
 inline Shared& blk_sm(int b) { return g_sim_sms[b]; }
+inline Shared* remote_blk(int t) { return &g_sim_sms[local_block(0, t)]; }   // a "remote" block is just another one here
 inline Tables& my_tb() { return *g_sim_tb; }
 inline int gang_live() { return g_sim_nlive; }
 #endif
-#define my_sm() blk_sm(HEVCE_SLOT * NTRACK + HEVCE_TRK)                /* the executing track's block       */
-#define pic_sm() blk_sm(HEVCE_SLOT * NTRACK)                          /* the picture-level state           */
-#define gang_sm(p) blk_sm((p) * NTRACK)                               /* picture p of the gang (track 0)   */
+#define my_sm() blk_sm(local_block(HEVCE_SLOT, HEVCE_TRK))             /* the executing track's block       */
+#define pic_sm() blk_sm(picture_block(HEVCE_SLOT, HEVCE_TRK))          /* the picture-level state (cluster: this track's mirror) */
+#define gang_sm(p) blk_sm(local_block((p), 0))                         /* picture p of the gang (track 0)   */
 static_assert(AUX_CODER + NREC * (int)sizeof(Coder) <= POOL_BYTES, "pool tail too small");
 
 // ---- thread <-> work mappings (shared by the kernel and the simulators) --------------------------------------------
@@ -649,9 +694,21 @@ enum { BAR_TEAM_A = 1, BAR_TEAM_B = 2, BAR_PICTURES = 3, BAR_TRACK0 = 4, BAR_RDV
 #define GANG_FOR_UPPER_FREE(it, first, n) for (int st_ = 1, it = upper_free_first(upper_index(HEVCE_SLOT, HEVCE_TID), (first), gang_live(), (n), st_); it < (n); it += st_)
 // end of a phase: the threads of this track (of all live pictures); without tracks that is every live thread
 #define PHASE_END() do { if (TRACKS) HEVCE_BAR(BAR_TRACK0 + HEVCE_TRK, gang_live() * trk_size(HEVCE_TRK)); else HEVCE_BAR(BAR_PICTURES, gang_live() * NT); } while (0)
-#define BAR_ALL() HEVCE_BAR(BAR_PICTURES, gang_live() * NT)
-// rendezvous of track 0 with parent track t (a no-op for the third track)
-#define TRACK_RDV(t) do { if (HEVCE_TRK == 0 || HEVCE_TRK == (t)) HEVCE_BAR(BAR_RDV1 - 1 + (t), gang_live() * (TRK_C + TRK_P)); } while (0)
+// picture-wide phases (CTU load / store): every thread of the picture; in the cluster variant the threads of rank 0 (= track 0)
+#define BAR_ALL() do { if (!CLUSTER) HEVCE_BAR(BAR_PICTURES, gang_live() * NT); else if (HEVCE_TRK == 0) PHASE_END(); } while (0)
+#define PAR_FOR_ALL_OWNER (!CLUSTER || HEVCE_TRK == 0)
+// Rendezvous of track 0 with parent track t (no-ops for the third track).  START: the node's entry snapshot exists, track t may
+// evaluate the node's candidates; END: track t has finished, track 0 may decide.  One CTA: a named barrier over both tracks.
+// Cluster: track 0 pushes the picture state into track t's block, then raises a flag in it (release / acquire at cluster
+// scope, sequence numbers instead of resets); at the END track t raises a flag in track 0's block.
+#define TRACK_START(t, seq) do { \
+    if (!CLUSTER) { if (HEVCE_TRK == 0 || HEVCE_TRK == (t)) HEVCE_BAR(BAR_RDV1 - 1 + (t), gang_live() * (TRK_C + TRK_P)); } \
+    else if (HEVCE_TRK == 0) { PHASE_END(); push_picture_state(t); PHASE_END(); if (HEVCE_TID == 0) rdv_signal(&remote_blk(t)->rdv_seq[0], (seq)); } \
+    else if (HEVCE_TRK == (t)) { if (HEVCE_TID == 0) rdv_wait(&my_sm().rdv_seq[0], (seq)); PHASE_END(); } } while (0)
+#define TRACK_END(t, seq) do { \
+    if (!CLUSTER) { if (HEVCE_TRK == 0 || HEVCE_TRK == (t)) HEVCE_BAR(BAR_RDV1 - 1 + (t), gang_live() * (TRK_C + TRK_P)); } \
+    else if (HEVCE_TRK == (t)) { PHASE_END(); if (HEVCE_TID == 0) rdv_signal(&remote_blk(0)->rdv_seq[t], (seq)); } \
+    else if (HEVCE_TRK == 0) { if (HEVCE_TID == 0) rdv_wait(&my_sm().rdv_seq[t], (seq)); PHASE_END(); } } while (0)
 #define ON_TRACK(t) if (HEVCE_TRK == (t))
 // between the pixel phases A..D of one round: all lines of a candidate's TU are work items of the same warp (T <= 32
 // consecutive items, groups start at multiples of T), so the hand-over needs no CTA- or team-wide barrier
@@ -693,13 +750,16 @@ inline int sim_item(int i, int n) {
 // picture-wide barriers are real.  Inside a track the phases run sequentially (teams one after the other).
 extern thread_local int g_sim_my_track;                              // the track this host thread stands for
 #define ON_TRACK(t) if (g_sim_my_track == (t) && ((g_sim_trk = (t)), true))
-#define TRACK_RDV(t) do { if (g_sim_my_track == 0 || g_sim_my_track == (t)) sim_barrier(BAR_RDV1 - 1 + (t), 2); } while (0)
-#define BAR_ALL() sim_barrier(BAR_PICTURES, NTRACK)
+#define TRACK_START(t, seq) do { if (g_sim_my_track == 0) { g_sim_trk = 0; if (CLUSTER) push_picture_state(t); } \
+    if (g_sim_my_track == 0 || g_sim_my_track == (t)) sim_barrier(BAR_RDV1 - 1 + (t), 2); } while (0)
+#define TRACK_END(t, seq) do { if (g_sim_my_track == 0 || g_sim_my_track == (t)) sim_barrier(BAR_RDV1 - 1 + (t), 2); } while (0)
+#define BAR_ALL() do { if (!CLUSTER) sim_barrier(BAR_PICTURES, NTRACK); } while (0)   /* cluster: the parent tracks only meet track 0 at the rendezvous */
 #define PAR_FOR_ALL_OWNER (g_sim_my_track == 0)                       /* picture-wide loops: run once, by track 0's thread */
 #else
 // tracks one after the other on the calling thread: a parent's candidates right after its snapshot, then the children
 #define ON_TRACK(t) if ((g_sim_trk = (t)), true)
-#define TRACK_RDV(t) ((void)(g_sim_trk = 0))
+#define TRACK_START(t, seq) do { g_sim_trk = 0; if (CLUSTER) push_picture_state(t); } while (0)
+#define TRACK_END(t, seq) ((void)(g_sim_trk = 0))
 #define PAR_FOR_ALL_OWNER true
 #endif
 #if defined(HEVCE_SIM_GANG)
@@ -742,9 +802,15 @@ extern thread_local int g_sim_my_track;                              // the trac
 #endif
 #endif
 #endif
-#if defined(__CUDA_ARCH__) || defined(__CUDACC__)
-#define PAR_FOR_ALL_OWNER true
-#endif
+
+// Cluster variant, on track 0's threads: the picture-level state [ctx0, mirror_end) into track t's block (another CTA's
+// shared memory, written through distributed shared memory) before track t is released to evaluate a node.
+HEVCE_HD inline void push_picture_state(int t) {
+    const Shared& sm = my_sm();
+    Shared* dst = remote_blk(t);
+    const int w0 = (int)((const u8*)sm.ctx0 - (const u8*)&sm) / 4, w1 = (int)((const u8*)&sm.mirror_end - (const u8*)&sm) / 4;
+    PAR_FOR(i, w1 - w0) ((u32*)dst)[w0 + i] = ((const u32*)&sm)[w0 + i];
+}
 
 struct Avail { int L, LB, A, AR; };
 HEVCE_HD inline Avail sub_avail(const Avail& a, int k) {   // HEVCe.c:1376-1379
@@ -1484,8 +1550,8 @@ HEVCE_HD inline int sm_off(const Shared& sm, const void* p) { return (int)((cons
 // candidates 70..104 are NxN PU modes: residual alone from a fresh coder and fresh contexts (HEVCe.c:1505-1519).
 template <int S>
 HEVCE_HD inline void trial_lane(int pic, int trk, int cand, int depth, int y0, int x0) {
-    Shared& sm = blk_sm(pic * NTRACK + trk);         // the track's block: lane contexts, candidate results, scratch
-    const Shared& pm = blk_sm(pic * NTRACK);         // the picture: maps, snapshots
+    Shared& sm = blk_sm(local_block(pic, trk));      // the track's block: lane contexts, candidate results, scratch
+    const Shared& pm = blk_sm(picture_block(pic, trk));   // the picture: maps, snapshots
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
     const int split_ctx = (S > pm.msz[my * 9 + mx - 1]) + (S > pm.msz[(my - 1) * 9 + mx]);
     const int pmL = pm.mpm[my * 9 + mx - 1], pmA = pm.mpm[(my - 1) * 9 + mx];
@@ -1519,7 +1585,7 @@ HEVCE_HD inline void trial_lane(int pic, int trk, int cand, int depth, int y0, i
     } else {
         d.lev[0] = lev; d.mlo[0] = sm.cgnz[cand][0]; d.mhi = pu ? 0u : sm.cgnz[cand][1];
     }
-    code_cu<Bac, MainEnv>(b, pic * NTRACK + trk, sm_off(sm, sm.lane_ctx + slot), 4 * NLANE, d);
+    code_cu<Bac, MainEnv>(b, local_block(pic, trk), sm_off(sm, sm.lane_ctx + slot), 4 * NLANE, d);
     const int bits = coder_len(b.c) - base_len;
     if (pu) sm.cand_bits[cand] = bits;
     else {   // the lane leaves its RD cost (the distortion is complete since phase D) and its end state
@@ -1541,7 +1607,7 @@ HEVCE_HD inline void nxn_trial(Shared& sm, int pic, int depth, int y0, int x0) {
     d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
     d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
     d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
-    code_cu<Bac, MainEnv>(b, pic * NTRACK, sm_off(sm, sm.nxn_ctx), 4, d);
+    code_cu<Bac, MainEnv>(b, local_block(pic, 0), sm_off(sm, sm.nxn_ctx), 4, d);
     int sse = 0;
     for (int y = 0; y < 8; y++)
         for (int x = 0; x < 8; x++) { const int dd = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += dd * dd; }
@@ -1716,8 +1782,9 @@ HEVCE_HD HEVCE_NOINLINE void eval_candidates(int q, int y0, int x0, const Avail&
 template <int S>
 HEVCE_HD HEVCE_NOINLINE void decide_adopt(int q, int y0, int x0, int depth) {
     Shared& sm = my_sm();
-    Shared& cm = blk_sm(HEVCE_SLOT * NTRACK + TrackOf<S>::value);
-    const Scratch sc = cm.sc;
+    constexpr int CT = TrackOf<S>::value;
+    Shared& cm = CT == 0 ? sm : *remote_blk(CT);   // the evaluating track's block (cluster variant: in the other CTA)
+    const Scratch sc = sm.sc_of[CT];
     constexpr int N4 = S / 4;
     const RdK rk = rd_consts(q);
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
@@ -1728,6 +1795,7 @@ HEVCE_HD HEVCE_NOINLINE void decide_adopt(int q, int y0, int x0, int depth) {
             for (int x = 0; x < S; x++) { const int d = (int)sm.orig[(y0 + row) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + row, x0 + x); acc += d * d; }
             sm.part_sse[row] = acc;
         }
+        if (CT != 0) PAR_FOR(c, 2 * NMODE) sm.cand_bits[c] = cm.cand_bits[c];   // the parent track's RD costs, fetched in parallel
         PHASE_END_T(P_DECIDE);
     }
 
@@ -1740,7 +1808,7 @@ HEVCE_HD HEVCE_NOINLINE void decide_adopt(int q, int y0, int x0, int depth) {
             best = rd_cost(rk, sse, coder_len(sm.live) - coder_len(sm.snap[depth]));
         }
         for (int c = 0; c < 2 * NMODE; c++) {   // one-TU modes 0..34, then four-TU modes 0..34 (HEVCe.c:1440, 1476)
-            const int cost = cm.cand_bits[c];   // RD cost, left by the candidate's trial lane
+            const int cost = sm.cand_bits[c];   // RD cost, left by the candidate's trial lane
             if (best >= cost) { best = cost; win = c; }
         }
         if (S == 8 && best >= sm.nxn_cost) win = NCAND;   // HEVCe.c:1546
@@ -1926,7 +1994,10 @@ HEVCE_HD inline void encode_picture(const Job& job, const Scratch* scs) {
     }
     PIC_FOR(i, 81) { sm.msz[i] = CTU; sm.mpm[i] = 1; }
     PIC_FOR(i, W / 4) sc.msz_line[i] = CTU;
-    PIC_FOR(t, NTRACK) blk_sm(HEVCE_SLOT * NTRACK + t).sc = scs[t];
+    for (int t = 0; t < NTRACK; t++)
+        ON_TRACK(t) PAR_FOR(one, 1) my_sm().sc = scs[t];    // every track: its own scratch
+    ON_TRACK(0) PAR_FOR(t, NTRACK) sm.sc_of[t] = scs[t];
+    unsigned rdv1 = 0, rdv2 = 0;                            // rendezvous counters (uniform over the threads of a track)
     PIC_FOR(one, 1) {
         coder_reset(sm.live);
         sm.error = 0;
@@ -1976,13 +2047,13 @@ HEVCE_HD inline void encode_picture(const Job& job, const Scratch* scs) {
                 // Parent || child: as soon as a node's entry snapshot exists (rendezvous), its own candidates are evaluated
                 // on the node size's track while track 0 walks the children; the decision waits for both (second rendezvous).
                 ON_TRACK(0) enter_node<32>(sm, 0, 0, 0);
-                TRACK_RDV(2);
+                TRACK_START(2, ++rdv2);
                 ON_TRACK(2) eval_candidates<32>(q, 0, 0, av, 0);
                 for (int a = 0; a < 4; a++) {
                     const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
                     const Avail av16 = sub_avail(av, a);
                     ON_TRACK(0) enter_node<16>(sm, y16, x16, 1);
-                    TRACK_RDV(1);
+                    TRACK_START(1, ++rdv1);
                     ON_TRACK(1) eval_candidates<16>(q, y16, x16, av16, 1);
                     ON_TRACK(0) {
                         for (int c = 0; c < 4; c++) {
@@ -1991,10 +2062,10 @@ HEVCE_HD inline void encode_picture(const Job& job, const Scratch* scs) {
                             eval_node<8>(q, y8, x8, sub_avail(av16, c), 2);
                         }
                     }
-                    TRACK_RDV(1);
+                    TRACK_END(1, rdv1);
                     ON_TRACK(0) decide_adopt<16>(q, y16, x16, 1);
                 }
-                TRACK_RDV(2);
+                TRACK_END(2, rdv2);
                 ON_TRACK(0) decide_adopt<32>(q, 0, 0, 0);
                 BAR_ALL();
             }

@@ -132,7 +132,7 @@ void variants_init() {
     std::call_once(g_variants_once, [] {
         fill_tables(g_host_tables);
         // relative per-CTU latency of a gang (all SMs busy with the same variant), measured on B200 -- profiles/r2_notes.md
-        static const double kCost[NVARIANT] = {1.00, 0.74, 0.63, 0.54, 0.52};   // 8.63 / 6.38 / 5.42 / 4.65 / 4.46 ms per CTU, 148 gangs of 64x64 pictures, qpd6=2
+        static const double kCost[NVARIANT] = {1.00, 0.74, 0.63, 0.54, 0.52, 0.30};   // 8.63 / 6.38 / 5.42 / 4.65 / 4.46 / 2.61 ms per CTU of one gang (148 gangs of 64x64 pictures, 74 for c2), qpd6=2
         for (int v = 0; v < NVARIANT; v++) { g_variants[v].info(&g_variants[v].vi); g_variants[v].cost = kCost[v]; }
         if (const char* env = getenv("HEVCE_VARIANT"))
             for (int v = 0; v < NVARIANT; v++) if (!strcmp(env, g_variants[v].name)) g_forced_variant = v;
@@ -272,7 +272,7 @@ static int choose_variant(int sms, const std::vector<Job>& jobs, const std::vect
     if (best >= 0) return best;
     double best_t = 0;
     for (int v = 0; v < NVARIANT; v++) {
-        const double t = (double)build_gangs(jobs, order, g_variants[v].vi.gang, sms, nullptr) * g_variants[v].cost;
+        const double t = (double)build_gangs(jobs, order, g_variants[v].vi.gang, sms / g_variants[v].vi.cluster, nullptr) * g_variants[v].cost;
         if (best < 0 || t < best_t) { best = v; best_t = t; }
     }
     return best;
@@ -343,9 +343,10 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     s->variant = best;
     const int GANGV = g_variants[best].vi.gang;
     std::vector<int> gangs;
-    build_gangs(s->jobs, s->order, GANGV, di.sms, &gangs);
+    const int CLV = g_variants[best].vi.cluster;          // CTAs per gang
+    build_gangs(s->jobs, s->order, GANGV, di.sms / CLV, &gangs);
     s->ngangs = (int)gangs.size() / GANGV;
-    s->grid = std::min(s->ngangs, di.sms);
+    s->grid = std::min(s->ngangs, di.sms / CLV) * CLV;
     if ((rc = grow(&s->d_img, &s->c_img, io))) return rc;
     if ((rc = grow(&s->d_rcon, &s->c_rcon, ro))) return rc;
     if ((rc = grow(&s->d_out, &s->c_out, oo))) return rc;
@@ -353,7 +354,7 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     if ((rc = grow(&s->d_order, &s->c_order, gangs.size()))) return rc;
     if ((rc = grow(&s->d_results, &s->c_results, (size_t)2 * n))) return rc;
     if (!s->d_counter) CK(cudaMalloc((void**)&s->d_counter, sizeof(int)));
-    const size_t g = (size_t)s->grid * GANGV * g_variants[best].vi.tracks, nlev = (size_t)NCAND * LEV_STRIDE + 64, nrec = (size_t)NREC * CTU * CTU;
+    const size_t g = (size_t)(s->grid / CLV) * GANGV * g_variants[best].vi.tracks, nlev = (size_t)NCAND * LEV_STRIDE + 64, nrec = (size_t)NREC * CTU * CTU;
     s->line_pitch = maxW / 4 + 32;
     if ((rc = grow(&s->d_glev, &s->c_glev, g * nlev))) return rc;
     if ((rc = grow(&s->d_grec, &s->c_grec, g * nrec))) return rc;

@@ -8,6 +8,7 @@ typedef struct hevce_variant_info {
     int lanes_per_warp;        /* trial-coder lanes hosted by one warp               */
     int wide;                  /* 1: one picture per CTA with the large pool         */
     int tracks;                /* thread tracks per picture (3 = parent || child)    */
+    int cluster;               /* CTAs (SMs) per picture: 1, or 2 = tracks on a cluster */
     long long smem_bytes;      /* dynamic shared memory per CTA                      */
 } hevce_variant_info;
 
@@ -17,7 +18,8 @@ typedef struct hevce_variant_info {
     X(g4, 4, 224, 24, 0)      \
     X(g2, 2, 448, 16, 0)       \
     X(w1, 1, 896, 8, 1)       \
-    X(t1, 1, 896, 12, 0)
+    X(t1, 1, 896, 12, 0)      \
+    X(c2, 1, 896, 8, 0)
 
 #ifdef __cplusplus
 extern "C" {

@@ -71,8 +71,9 @@ HEVCE_API void hevce_release(void);
 /* Kernel variant for the batches configured from now on.  The decision kernel is linked in four variants of the same
  * source: "g7" / "g4" / "g2" = 7 / 4 / 2 same-size pictures per CTA in lock-step (throughput), "w1" = one picture per
  * CTA with all its threads and nearly all shared memory of the SM, "t1" = one picture per CTA whose threads form three
- * tracks so that a 16x16 / 32x32 node's own candidates are evaluated while its children are decided (latency: few or
- * large pictures).  NULL, "" or
+ * tracks so that a 16x16 / 32x32 node's own candidates are evaluated while its children are decided, "c2" = the same
+ * tracks on a cluster of two CTAs (two SMs per picture, state exchanged through distributed shared memory; latency: few
+ * or large pictures).  NULL, "" or
  * "auto" (default; also the environment variable HEVCE_VARIANT) chooses per batch.  Every variant produces the same
  * bytes.  returns 0, or HEVCE_ERR_ARG for an unknown name. */
 HEVCE_API int hevce_set_variant(const char *name);

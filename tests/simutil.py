@@ -13,8 +13,9 @@ _u8p = ctypes.POINTER(ctypes.c_ubyte)
 
 
 # kernel variants (csrc/Makefile, hevce_variants.h): tag -> (pictures per CTA, threads per picture, lanes per warp, wide)
-VARIANTS = {"g7": (7, 128, 32, 0), "g4": (4, 224, 24, 0), "g2": (2, 448, 16, 0), "w1": (1, 896, 8, 1), "t1": (1, 896, 12, 0)}
-TRACK_FLAGS = {"t1": ["-DHEVCE_OPT_TRACKS=1", "-DHEVCE_OPT_TRK_C=448", "-DHEVCE_OPT_LPW_P=24"]}   # parent || child variants
+VARIANTS = {"g7": (7, 128, 32, 0), "g4": (4, 224, 24, 0), "g2": (2, 448, 16, 0), "w1": (1, 896, 8, 1), "t1": (1, 896, 12, 0), "c2": (1, 896, 8, 0)}
+TRACK_FLAGS = {"t1": ["-DHEVCE_OPT_TRACKS=1", "-DHEVCE_OPT_TRK_C=448", "-DHEVCE_OPT_LPW_P=24"],       # parent || child variants
+               "c2": ["-DHEVCE_OPT_TRACKS=1", "-DHEVCE_OPT_CLUSTER=2", "-DHEVCE_OPT_LPW_P=8"]}
 
 
 def variant_flags(variant):

@@ -12,7 +12,7 @@ import refutil as R
 import workloads as WL
 
 pytestmark = pytest.mark.gpu
-VARIANTS = ("g7", "g4", "g2", "w1", "t1")
+VARIANTS = ("g7", "g4", "g2", "w1", "t1", "c2")
 
 
 @pytest.fixture(scope="module")
@@ -76,7 +76,7 @@ def test_variants_agree_on_kodak_size(H):
 def test_automatic_choice(H):
     H.set_variant(None)
     shape = [(64, 64)]
-    for n, want in ((1, ("w1", "t1")), (100, ("w1", "t1")), (148 * 7, ("g7",)), (148 * 7 * 3, ("g7",))):
+    for n, want in ((1, ("w1", "t1", "c2")), (100, ("w1", "t1", "c2")), (148 * 7, ("g7",)), (148 * 7 * 3, ("g7",))):
         ses = H.Session(0, shape * n, 2)
         got = ses.variant
         ses.close()

@@ -105,20 +105,23 @@ def test_wide_variant_single_thread_simulator_permuted():
         assert err == 0 and s == so and np.array_equal(r, ro), (q, order)
 
 
-def test_track_simulator_matches_oracle():
-    """Parent || child variant t1: one host thread per track, real rendezvous; a 64x96 crop and a padded 45x70 picture
-    at every qpd6 against the oracle."""
+@pytest.mark.parametrize("variant", ["t1", "c2"])
+def test_track_simulator_matches_oracle(variant):
+    """Parent || child variants (t1: three tracks in one CTA; c2: the tracks on a two-CTA cluster, picture state pushed into
+    the parent tracks' blocks, results fetched back): one host thread per track, real rendezvous; a 64x96 crop and a padded
+    45x70 picture at every qpd6 against the oracle."""
     for k, (h, w) in enumerate(((64, 96), (45, 70))):
         img = crops(1, h, w)[0]
         for q in range(5):
-            s, r, err = S.simtrack_encode(img, q, order=(0, 3)[(q + k) % 2])
+            s, r, err = S.simtrack_encode(img, q, order=(0, 3)[(q + k) % 2], variant=variant)
             so, ro = R.oracle_encode(img, q)
-            assert err == 0 and s == so and np.array_equal(r, ro), (h, w, q)
-            s1, r1, e1 = S.sim_encode(img, q, variant="t1")      # the same variant with its tracks one after the other
+            assert err == 0 and s == so and np.array_equal(r, ro), (variant, h, w, q)
+            s1, r1, e1 = S.sim_encode(img, q, variant=variant)    # the same variant with its tracks one after the other
             assert (s1, e1) == (s, err) and np.array_equal(r1, r)
 
 
-def test_tracks_share_no_unsynchronised_data_under_thread_sanitizer(tmp_path):
+@pytest.mark.parametrize("variant", ["t1", "c2"])
+def test_tracks_share_no_unsynchronised_data_under_thread_sanitizer(tmp_path, variant):
     """ThreadSanitizer over the track simulator: the 16x16 / 32x32 candidate tracks run beside the 8x8 chain."""
     probe = tmp_path / "probe.cpp"
     probe.write_text("#include <thread>\nint x;int main(){std::thread a([]{for(int i=0;i<100000;i++)x++;});"
@@ -146,7 +149,7 @@ int main() {
 }
 ''')
     exe = tmp_path / "tsan_tracks"
-    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", *S.variant_flags("t1"), "-I", S.CSRC,
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", *S.variant_flags(variant), "-I", S.CSRC,
                     "-o", str(exe), str(main), os.path.join(S.SIM_DIR, "hevce_simtrack.cpp")], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0 and "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]

@@ -12,12 +12,12 @@ import hevce_b200 as H  # noqa: E402
 import workloads as WL  # noqa: E402
 
 h, w, q = (int(v) for v in (sys.argv[1:4] + ["64", "64", "2"][len(sys.argv[1:4]):]))
-variants = sys.argv[4:] or ["g7", "g4", "g2", "w1", "t1"]
-gang = {"g7": 7, "g4": 4, "g2": 2, "w1": 1, "t1": 1}
+variants = sys.argv[4:] or ["g7", "g4", "g2", "w1", "t1", "c2"]
+gang = {"g7": 7, "g4": 4, "g2": 2, "w1": 1, "t1": 1, "c2": 0.5}
 K = WL.kodak_landscape()
 base = None
 for v in variants:
-    n = 148 * gang[v]
+    n = int(148 * gang[v])
     imgs = [WL.config3_image(i, K)[(37 * i) % (512 - h + 1):, (53 * i) % (768 - w + 1):][:h, :w].copy() for i in range(n)]
     H.set_variant(v)
     ses = H.Session(0, [i.shape for i in imgs], q)
