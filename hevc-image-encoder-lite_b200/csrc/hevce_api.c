@@ -5,9 +5,9 @@
  *   HEVCImageEncoderBatch  n independent pictures, sharded over the selected GPUs by cumulative CTU count,
  *                          no collective
  *
- * A shard (the pictures of one device) is cut into chunks -- whole kernel waves for large shards, four parts for up to
- * four waves -- and two to four host threads per device take chunks in turn, each with its own session (stream + pinned
- * staging), so the host<->device copies of one chunk overlap the kernels of the others, whose CTAs share the SMs.
+ * A shard (the pictures of one device) is cut into chunks; same-size pictures run as rounds of four chunks on four host
+ * threads, each with its own session (stream + pinned staging) and its kernel on a quarter of the SMs, so the
+ * host<->device copies of one chunk overlap the kernels of the others.
  *
  * There is no CPU encoder in this library: every picture is encoded by the sm_100a kernels; if no CUDA device can be
  * used the calls fail with HEVCE_ERR_CUDA.
@@ -134,7 +134,7 @@ API void hevce_release(void) {
 }
 
 typedef struct {
-    int device, first, count, status, max_dim, variant;
+    int device, first, count, status, max_dim, variant, max_ctas;
     unsigned char *const *pbuffers;
     const unsigned char *const *imgs;
     unsigned char *const *rcons;
@@ -170,7 +170,7 @@ static void *chunk_worker(void *arg) {
         if (c >= sh->nchunk) break;
         a = sh->chunk_first[c];
         m = sh->chunk_first[c + 1] - a;
-        rc = hevce_session_configure(s, m, sh->ysz + a, sh->xsz + a, sh->qpd6 + a, sh->max_dim, sh->variant);
+        rc = hevce_session_configure(s, m, sh->ysz + a, sh->xsz + a, sh->qpd6 + a, sh->max_dim, sh->variant, sh->max_ctas);
         if (!rc) rc = hevce_session_upload(s, sh->imgs + a);
         if (!rc) rc = hevce_session_encode(s);
         if (!rc) rc = hevce_session_download(s, sh->pbuffers + a, sh->rcons + a, sh->stream_len + a);
@@ -200,14 +200,28 @@ static void *shard_main(void *arg) {
     sh->variant = hevce_internal_choose_variant(sh->device, sh->count, sh->ysz + sh->first, sh->xsz + sh->first, sh->max_dim);
     for (i = 1; i < sh->count && same; i++)
         if (sh->ysz[sh->first + i] != sh->ysz[sh->first] || sh->xsz[sh->first + i] != sh->xsz[sh->first]) same = 0;
-    if (same && sh->count >= 8 * 7 && sh->count <= MAX_WORKERS * WAVE_PICTURES &&
-        padded_pixels(sh->ysz[sh->first], sh->xsz[sh->first], sh->max_dim) * sh->count <= MAX_WORKERS * CHUNK_PIXELS) {
-        /* up to four waves of same-size pictures: four chunks (multiples of 7 pictures) on four workers whose kernels share
-           the SMs, so the upload of a chunk overlaps the kernels of the chunks before it and the downloads are staggered */
-        int per = (sh->count + MAX_WORKERS - 1) / MAX_WORKERS;
+    sh->max_ctas = 0;
+    if (same && sh->count >= 8 * 7) {
+        /* Same-size pictures: rounds of four chunks (multiples of 7 pictures) on four workers, every chunk's kernel on a
+           quarter of the SMs.  The four kernels run side by side, so the copies of a chunk overlap the kernels of the
+           others, and the small commit kernel that follows a chunk's decision kernel finds that chunk's SMs free (behind
+           whole-device kernels it would wait for the next chunk's persistent CTAs to finish). */
+        const long long px = padded_pixels(sh->ysz[sh->first], sh->xsz[sh->first], sh->max_dim) * sh->count;
+        int rounds = (int)((px + MAX_WORKERS * CHUNK_PIXELS - 1) / (MAX_WORKERS * CHUNK_PIXELS)), per, nch, sms = hevce_internal_device_sms(sh->device);
+        if (rounds < 1) rounds = 1;
+        nch = rounds * MAX_WORKERS;
+        per = (sh->count + nch - 1) / nch;
         per = (per + 6) / 7 * 7;
         nworkers = MAX_WORKERS;
-        while (done < sh->count) {
+        /* more than one wave: cap every chunk's grid at a quarter of the SMs (smaller shards fit side by side anyway) */
+        sh->max_ctas = (sms > 0 && sh->count > WAVE_PICTURES) ? (sms + MAX_WORKERS - 1) / MAX_WORKERS : 0;
+        while (nch + 1 > cap) {
+            int *p = (int *)realloc(sh->chunk_first, sizeof(int) * (size_t)(2 * cap + 1));
+            if (!p) { sh->status = HEVCE_ERR_ARG; break; }
+            sh->chunk_first = p;
+            cap *= 2;
+        }
+        while (!sh->status && done < sh->count) {
             sh->chunk_first[sh->nchunk++] = sh->first + done;
             done += per < sh->count - done ? per : sh->count - done;
         }

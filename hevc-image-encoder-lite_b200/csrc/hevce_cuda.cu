@@ -304,7 +304,11 @@ extern "C" int hevce_internal_choose_variant(int device, int n, const int* ysz, 
     return choose_variant(g_dev[device].sms, jobs, order);
 }
 
-extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, const int* xsz, const int* qpd6, int max_dim, int variant) {
+extern "C" int hevce_internal_device_sms(int device) { return device_prepare(device) ? 0 : g_dev[device].sms; }
+
+// variant < 0: choose for this batch; max_ctas > 0: the launch uses at most that many CTAs (a chunk that shares the device
+// with other chunks' kernels)
+extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, const int* xsz, const int* qpd6, int max_dim, int variant, int max_ctas) {
     if (!s || n < 0 || n > 65535 || (n > 0 && (!ysz || !xsz || !qpd6))) return HEVCE_ERR_ARG;   // grid.y of the commit kernel = picture index
     int rc = device_prepare(s->device);
     if (rc) return rc;
@@ -346,7 +350,7 @@ extern "C" int hevce_session_configure(hevce_session* s, int n, const int* ysz, 
     const int CLV = g_variants[best].vi.cluster;          // CTAs per gang
     build_gangs(s->jobs, s->order, GANGV, di.sms / CLV, &gangs);
     s->ngangs = (int)gangs.size() / GANGV;
-    s->grid = std::min(s->ngangs, di.sms / CLV) * CLV;
+    s->grid = std::min(s->ngangs, std::max(1, (max_ctas > 0 ? std::min(max_ctas, di.sms) : di.sms) / CLV)) * CLV;
     if ((rc = grow(&s->d_img, &s->c_img, io))) return rc;
     if ((rc = grow(&s->d_rcon, &s->c_rcon, ro))) return rc;
     if ((rc = grow(&s->d_out, &s->c_out, oo))) return rc;
@@ -399,7 +403,7 @@ extern "C" hevce_session* hevce_session_create_empty(int device) {
 
 extern "C" hevce_session* hevce_session_create(int device, int n, const int* ysz, const int* xsz, const int* qpd6) {
     hevce_session* s = hevce_session_create_empty(device);
-    if (s && hevce_session_configure(s, n, ysz, xsz, qpd6, hevce_internal_max_dim(), -1)) { hevce_session_destroy(s); return nullptr; }
+    if (s && hevce_session_configure(s, n, ysz, xsz, qpd6, hevce_internal_max_dim(), -1, 0)) { hevce_session_destroy(s); return nullptr; }
     return s;
 }
 
