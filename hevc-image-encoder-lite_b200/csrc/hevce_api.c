@@ -286,7 +286,6 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
     for (i = 0; i < n; i++) total += padded_pixels(ysz[i], xsz[i], max_dim);
     /* contiguous shards with (nearly) equal padded-pixel = CTU counts */
     if (ndev > n) ndev = n;
-    hevce_internal_set_copy_threads(ndev > 1 ? (ndev >= 4 ? 1 : 2) : 4);   /* staging copies: up to 4 workers per shard share the host cores */
     for (k = 0, i = 0; k < ndev; k++) {
         int first = i;
         long long want = total * (k + 1) / ndev;

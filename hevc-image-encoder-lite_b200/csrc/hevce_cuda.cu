@@ -246,7 +246,14 @@ extern "C" void hevce_internal_set_device(int device) { if (device >= 0) cudaSet
 
 template <class F>
 static void parallel_pictures(int n, size_t total_bytes, F&& fn) {
-    unsigned nt = g_copy_threads > 0 ? (unsigned)g_copy_threads : std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    // default: the host cores shared by up to four chunk workers per device and by every visible device (one process per GPU
+    // or one process for all of them: either way about that many workers copy at the same time)
+    static const unsigned auto_threads = [] {
+        int nd = 1;
+        if (cudaGetDeviceCount(&nd) != cudaSuccess || nd < 1) nd = 1;
+        return std::min(4u, std::max(1u, std::thread::hardware_concurrency() / (4u * (unsigned)nd)));
+    }();
+    unsigned nt = g_copy_threads > 0 ? (unsigned)g_copy_threads : auto_threads;
     if (total_bytes < ((size_t)16 << 20) || n < 2 * (int)nt) nt = 1;
     if (nt == 1) { for (int i = 0; i < n; i++) fn(i); return; }
     std::vector<std::thread> th;
