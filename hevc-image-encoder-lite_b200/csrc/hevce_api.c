@@ -154,7 +154,7 @@ static long long padded_pixels(int h, int w, int max_dim) {
 /* worker: encode chunks of the shard until the queue is empty */
 static void *chunk_worker(void *arg) {
     Shard *sh = (Shard *)arg;
-    int slot, saved = hevce_internal_get_device();
+    int slot;
     hevce_session *s = pool_acquire(sh->device, &slot);
     if (!s) {
         pthread_mutex_lock(&sh->qlock);
@@ -181,7 +181,6 @@ static void *chunk_worker(void *arg) {
         }
     }
     pool_release(sh->device, slot, s);
-    hevce_internal_set_device(saved);   /* leave the caller's current device as it was */
     return NULL;
 }
 
@@ -264,7 +263,7 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
                               unsigned char *const *img_rcons, int *ysz, int *xsz, const int *qpd6, int *stream_len) {
     Shard shards[MAX_DEV];
     pthread_t threads[MAX_DEV];
-    int ndev, devs[MAX_DEV], i, k, nshard = 0, status = 0, *lens = stream_len;
+    int ndev, devs[MAX_DEV], i, k, nshard = 0, status = 0, *lens = stream_len, saved_device;
     const int max_dim = hevce_get_max_dim();   /* one value for the whole call: sharding, clamp and size write-back */
     long long total = 0, acc = 0;
     if (n < 0) return HEVCE_ERR_ARG;
@@ -283,6 +282,7 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
     }
     if (!lens) lens = (int *)malloc(sizeof(int) * (size_t)n);
     if (!lens) return HEVCE_ERR_ARG;
+    saved_device = hevce_internal_get_device();   /* shard 0 runs on this thread and selects its device */
     for (i = 0; i < n; i++) total += padded_pixels(ysz[i], xsz[i], max_dim);
     /* contiguous shards with (nearly) equal padded-pixel = CTU counts */
     if (ndev > n) ndev = n;
@@ -309,6 +309,7 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
             xsz[i] = ((xsz[i] < max_dim ? xsz[i] : max_dim) + 31) / 32 * 32;
         }
     if (lens != stream_len) free(lens);
+    hevce_internal_set_device(saved_device);      /* leave the caller's current device as it was */
     return status;
 }
 
