@@ -208,6 +208,7 @@ static void *shard_main(void *arg) {
         const long long px = padded_pixels(sh->ysz[sh->first], sh->xsz[sh->first], sh->max_dim) * sh->count;
         int rounds = (int)((px + MAX_WORKERS * CHUNK_PIXELS - 1) / (MAX_WORKERS * CHUNK_PIXELS)), per, nch, sms = hevce_internal_device_sms(sh->device);
         if (rounds < 1) rounds = 1;
+        while ((long long)rounds * MAX_WORKERS * (CHUNK_PICTURES - 7) < sh->count) rounds++;   /* many tiny pictures: the per-chunk picture bound */
         nch = rounds * MAX_WORKERS;
         per = (sh->count + nch - 1) / nch;
         per = (per + 6) / 7 * 7;
