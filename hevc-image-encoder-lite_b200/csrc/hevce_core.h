@@ -65,6 +65,22 @@
 #ifndef HEVCE_OPT_FASTREL
 #define HEVCE_OPT_FASTREL 0
 #endif
+// put_bin: one 32-bit table word per (context state, range quarter) carrying the LPS range, the LPS renormalisation
+// shift and both next states (one shared-memory load per bin instead of two or three plus the shift arithmetic)
+#ifndef HEVCE_OPT_BINTAB
+#define HEVCE_OPT_BINTAB 1
+#endif
+// Trial coder, byte release: the common case (exactly one pending byte, the new lead byte is not 0xFF, the released byte is
+// above 3 so neither an emulation-prevention byte nor a zero run is involved) as predicated straight-line code on every
+// bin; only the rare cases branch.  With 32 lanes per warp some lane releases a byte on nearly every bin, so the branchy
+// version is paid in full almost every time.
+#ifndef HEVCE_OPT_RELPRED
+#define HEVCE_OPT_RELPRED 0
+#endif
+// RDOQ evaluates the two candidate levels that can win (proof at phase_b_item); 0 = all three of HEVCe.c:571
+#ifndef HEVCE_OPT_RDOQ2
+#define HEVCE_OPT_RDOQ2 1
+#endif
 // ---- kernel variant (one translation unit per variant, see hevce_variant.cu): pictures per CTA, threads per picture,
 // trial lanes per warp and the pool plan.  GANG x NT threads run in lock-step phases; WIDE = one picture owns the CTA
 // and most of the SM's shared memory (all 35 candidates of a 16x16 / 32x32 step in one round).
@@ -132,18 +148,24 @@ constexpr int NTC = 128;           // threads per block of the commit kernel (on
 constexpr int NLANE = 70;          // trial-coder lanes with a private context set (the 35 NxN-PU lanes reuse 0..34)
 constexpr int NCAND = 105;         // trial-coder lanes of a CU node: 35 one-TU + 35 four-TU + 35 NxN-PU candidates
 constexpr int NMODE = 35;
-constexpr int NCTX = 104;          // context bytes: the contexts of HEVCe.c:745-759 that a luma-only intra stream can touch
-constexpr int CTXW = 26;           // context words per lane
+constexpr int NCTX = 91;           // context bytes: the contexts of HEVCe.c:745-759 that a luma-only intra stream can touch
+constexpr int CTXW = 23;           // context words per lane (odd: lane-major context sets of consecutive lanes start in different banks)
+constexpr int CTXW4 = 9;           // leading words that hold every context a 4x4 luma TU's residual can touch
 constexpr int WP = 65;             // pitch of the CTU reconstruction window (row 0 / col 0 = neighbours)
 constexpr int IMAX = 0x7fffffff;
 constexpr int LANE_ELEMS = CTU * CTU;
 
-// Compact layout (the reference struct also carries the chroma contexts, 142 bytes): split_cu 0-2, part 3, luma mode 4,
-// chroma mode 5, split_tu 6-8, cbf_luma 9-10, cbf_chroma 11, coded_sub_block 12-13, last_x 16-35 (4 sizes x 5), last_y
-// 36-55, sig_coeff 56-82 (27 luma), greater1 84-99 (4 sets x 4), greater2 100-103.  A 4x4 luma TU touches words
-// 4, 9, 14-16, 21-25 only.
-enum { CX_SPLIT_CU = 0, CX_PART = 3, CX_YPM = 4, CX_UVPM = 5, CX_SPLIT_TU = 6, CX_YCBF = 9, CX_UVCBF = 11, CX_SIGCG = 12,
-       CX_LASTX = 16, CX_LASTY = 36, CX_SIG = 56, CX_ONE = 84, CX_ABS = 100 };
+// Compact layout (the reference struct also carries the chroma contexts, 142 bytes).  What the residual of a 4x4 luma TU
+// touches comes first, so an NxN PU lane initialises words 0..CTXW4-1 only: last_x of 4x4 TUs 0-2, last_y of 4x4 TUs 3-5,
+// greater1 6-21 (4 sets x 4), greater2 22-25, sig_coeff 26-52 (27 luma; 4x4 TUs use the first 9); then split_cu 53-55,
+// part 56, luma mode 57, chroma mode 58, split_tu 59-61, cbf_luma 62-63, cbf_chroma 64, coded_sub_block 65-66, last_x of
+// 8x8 / 16x16 / 32x32 TUs 67-69 / 70-73 / 74-78 (only the 3 / 4 / 5 contexts a TU size can reach, HEVCe.c:1046-1075),
+// last_y 79-81 / 82-85 / 86-90.
+enum { CX_LASTX4 = 0, CX_LASTY4 = 3, CX_ONE = 6, CX_ABS = 22, CX_SIG = 26, CX_SPLIT_CU = 53, CX_PART = 56, CX_YPM = 57, CX_UVPM = 58,
+       CX_SPLIT_TU = 59, CX_YCBF = 62, CX_UVCBF = 64, CX_SIGCG = 65, CX_LASTX = 67, CX_LASTY = 79 };
+// first last_x / last_y context of a TU of size 4 << row
+HEVCE_HD inline int cx_lastx(int row) { return row == 0 ? CX_LASTX4 : row == 1 ? CX_LASTX : row == 2 ? CX_LASTX + 3 : CX_LASTX + 7; }
+HEVCE_HD inline int cx_lasty(int row) { return row == 0 ? CX_LASTY4 : row == 1 ? CX_LASTY : row == 2 ? CX_LASTY + 3 : CX_LASTY + 7; }
 
 HEVCE_HD inline int imin(int a, int b) { return a < b ? a : b; }
 HEVCE_HD inline int imax(int a, int b) { return a > b ? a : b; }
@@ -166,16 +188,19 @@ HEVCE_HD inline int bitlen(unsigned v) {
 struct Tables {
     u32 lps4[64];          // rangeTabLps, one word per state: byte q = LPS range for (range>>6)&3 == q  (HEVCe.c:704-713)
     u8 next_lps[128];      // (state<<1|mps) after an LPS                   (HEVCe.c:702)
+    u32 bin4[4 + 512];     // [4 + ctx*4 + q], ctx = state<<1|mps, q = (range>>6)&3 (range>>6 is 4..7, hence the 4 unused words in front):
+                           // byte 0 LPS range, byte 1 ctx after an LPS, byte 2 ctx after an MPS, bits 29..31 LPS renorm shift (HEVCe.c:701-715)
     u8 ctx_iv[4 * CTXW];   // context init values by (compact) context index    (HEVCe.c:763-777)
     u8 scan4[3][16];       // in-CG scan, (y<<2)|x : diag / horizontal / vertical
     u8 inv4[3][16];        // inverse: raster index (y<<2)|x -> scan index
-    u32 sigoff[3][4];      // sig_coeff ctx offset (2 bits per scan index) by neighbour pattern (HEVCe.c:1116-1121)
+    unsigned long long sigoff[3][4];   // sig_coeff ctx offset (4 bits per scan index) by neighbour pattern (HEVCe.c:1116-1121)
     unsigned long long sig4[3];   // sig_coeff ctx of 4x4 TUs (4 bits per scan index)
     u8 cgdiag[3][64];      // diagonal CG order for 2x2 / 4x4 / 8x8 CG grids, (cy<<3)|cx
     u8 sigp4[16];          // sig_coeff ctx for 4x4 TUs                     (HEVCe.c:1093)
     u8 grp[32];            // last-position group index                     (HEVCe.c:1047)
     u8 gmin[12];           // first position of a group                     (HEVCe.c:1048)
     int rate32[32];        // RDOQ rate estimate of levels 0..31                (HEVCe.c:526-535)
+    int drate[8];          // rate(l) - rate(l-1) for l = 1..6; [7] = 0: from 7 on the step is 65536 when l-5 is a power of two, else 0
 };
 
 inline void fill_tables(Tables& t) {
@@ -207,10 +232,17 @@ inline void fill_tables(Tables& t) {
     for (int s = 0; s < 64; s++) t.lps4[s] = (u32)LPS[s][0] | ((u32)LPS[s][1] << 8) | ((u32)LPS[s][2] << 16) | ((u32)LPS[s][3] << 24);
     for (int s = 0; s < 64; s++)
         for (int m = 0; m < 2; m++) t.next_lps[(s << 1) | m] = (u8)((TRANS_LPS[s] << 1) | (s == 0 ? !m : m));
+    for (int i = 0; i < 4; i++) t.bin4[i] = 0;
+    for (int v = 0; v < 128; v++)
+        for (int q = 0; q < 4; q++) {
+            const u32 lps = LPS[v >> 1][q], nb = lps < 8 ? 6 : 9 - bitlen(lps), nmps = v < 124 ? v + 2 : v;
+            t.bin4[4 + v * 4 + q] = lps | ((u32)t.next_lps[v] << 8) | (nmps << 16) | (nb << 29);
+        }
     // the init tables are in the reference's order (luma entries first in every group); only the luma part is kept
     for (int i = 0; i < 4 * CTXW; i++) t.ctx_iv[i] = 154;
-    for (int i = 0; i < 12; i++) t.ctx_iv[i] = HEAD[i];
-    for (int i = 0; i < 20; i++) t.ctx_iv[CX_LASTX + i] = t.ctx_iv[CX_LASTY + i] = LAST[i];
+    for (int i = 0; i < 12; i++) t.ctx_iv[CX_SPLIT_CU + i] = HEAD[i];   // split_cu .. cbf_chroma keep the reference's order
+    for (int row = 0; row < 4; row++)
+        for (int i = 0; i < (row < 2 ? 3 : row + 2); i++) t.ctx_iv[cx_lastx(row) + i] = t.ctx_iv[cx_lasty(row) + i] = LAST[5 * row + i];
     t.ctx_iv[CX_SIGCG] = 91;
     t.ctx_iv[CX_SIGCG + 1] = 171;
     for (int i = 0; i < 27; i++) t.ctx_iv[CX_SIG + i] = SIG[i];
@@ -231,12 +263,12 @@ inline void fill_tables(Tables& t) {
             t.sig4[type] |= (unsigned long long)P4[p4] << (4 * k);
         }
         for (int pat = 0; pat < 4; pat++) {
-            u32 w = 0;
+            unsigned long long w = 0;
             for (int k = 0; k < 16; k++) {
                 const int p4 = t.scan4[type][k], py = p4 >> 2, px = p4 & 3;
                 const int tt = pat == 0 ? py + px : pat == 1 ? 2 * py : 2 * px;
-                const u32 off = pat == 3 ? 2u : (tt == 0 ? 2u : tt < 3 ? 1u : 0u);
-                w |= off << (2 * k);
+                const unsigned long long off = pat == 3 ? 2u : (tt == 0 ? 2u : tt < 3 ? 1u : 0u);
+                w |= off << (4 * k);
             }
             t.sigoff[type][pat] = w;
         }
@@ -250,6 +282,7 @@ inline void fill_tables(Tables& t) {
     for (int i = 0; i < 16; i++) t.sigp4[i] = P4[i];
     for (int i = 0; i < 32; i++) t.grp[i] = (u8)(i < 4 ? i : i < 6 ? 4 : i < 8 ? 5 : i < 12 ? 6 : i < 16 ? 7 : i < 24 ? 8 : 9);
     for (int i = 0; i < 12; i++) t.gmin[i] = GMIN[i];
+    for (int l = 0; l < 8; l++) t.drate[l] = l == 1 ? 70000 : l == 2 ? 20000 : l == 3 ? 2000 : l == 4 ? 65536 : (l == 5 || l == 6) ? 32768 : 0;
     for (int l = 0; l < 32; l++)
         t.rate32[l] = l == 0 ? 0 : l == 1 ? 70000 : l == 2 ? 90000 : l == 3 ? 92000 : l == 4 ? 157536 : l == 5 ? 190304 : 92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15);
 }
@@ -296,6 +329,18 @@ struct BacT {
     Coder c;
     u8* out;            // EMIT only: destination of this CTU's bytes
     int cap;            // EMIT only: bytes available at out
+    u32 tabs;           // device: shared-space address of Tables::bin4, kept in a register (use_tables)
+
+    // The bin table is read with an explicit ld.shared from an address the compiler cannot re-derive: left to itself it
+    // rebuilds the shared-window base (S2UR + UMOV + ULEA) in front of every bin.
+    HEVCE_HD void use_tables(const Tables& tb) {
+#if defined(__CUDA_ARCH__) && HEVCE_OPT_BINTAB == 2
+        tabs = (u32)__cvta_generic_to_shared(&tb.bin4[0]);
+        asm volatile("mov.u32 %0, %0;" : "+r"(tabs));
+#else
+        (void)tb; tabs = 0;
+#endif
+    }
 
     HEVCE_HD void emit(int byte) {   // HEVCe.c:821-832
         const int b = byte & 0xff;
@@ -315,6 +360,23 @@ struct BacT {
         }
     }
     HEVCE_HD void carry_out() {   // HEVCe.c:859-879
+#if HEVCE_OPT_RELPRED
+        if (!EMIT) {
+            const bool rel = c.nbits < 12;
+            const int lead9 = c.low >> (24 - c.nbits);               // meaningful when rel (the shift count stays in 1..24 anyway)
+            const int b9 = (c.held + (lead9 >> 8)) & 0xff;
+            const bool common = (lead9 != 0xff) & (c.nbytes == 1) & (b9 > 3);
+            if (rel & common) {
+                c.nbits += 8;
+                c.low &= (int)(0xFFFFFFFFu >> c.nbits);
+                c.n += 1;
+                c.z = 0;
+                c.held = lead9 & 0xff;
+                return;
+            }
+            if (!rel) return;
+        }
+#endif
         if (c.nbits >= 12) return;
         const int lead = c.low >> (24 - c.nbits);
         c.nbits += 8;
@@ -356,6 +418,28 @@ struct BacT {
     }
     HEVCE_HD void put_bin(const Tables& tb, int bin, u8& cx) {   // HEVCe.c:914-933, both branches computed, then selected
         const int v = cx;
+#if HEVCE_OPT_BINTAB
+#if defined(__CUDA_ARCH__) && HEVCE_OPT_BINTAB == 2
+        u32 w;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(tabs + (u32)(v * 4 + (c.range >> 6)) * 4u));
+#else
+        const u32 w = tb.bin4[v * 4 + (c.range >> 6)];              // 256 <= range <= 510 between bins
+#endif
+        const int lps = (int)(w & 0xffu);
+        const int rmps = c.range - lps;
+        const bool is_lps = ((v ^ bin) & 1) != 0;                   // bin is 0 or 1 at every call site
+        const int sh = is_lps ? (int)(w >> 29) : (rmps < 256 ? 1 : 0);
+        if (is_lps) c.low += rmps;
+        c.low = (int)((unsigned)c.low << sh);
+        c.range = (is_lps ? lps : rmps) << sh;
+        c.nbits -= sh;
+        u32 nx = w >> 8;
+        if (!is_lps) nx >>= 8;
+        cx = (u8)nx;
+#if !defined(__CUDA_ARCH__)
+        if ((unsigned)bin > 1u || c.range < 256 || c.range > 510) __builtin_trap();
+#endif
+#else
 #if HEVCE_OPT_LPS4
         const int lps = (int)((tb.lps4[v >> 1] >> (((c.range >> 6) & 3) * 8)) & 0xffu);   // the load depends on the context only, not on range
 #else
@@ -364,8 +448,13 @@ struct BacT {
 #if HEVCE_OPT_BINSEL
         const int nlps = tb.next_lps[v];
         const int rmps = c.range - lps;
-        const bool is_lps = (bin != 0) != ((v & 1) != 0);
-        const int nb = lps < 8 ? 6 : 9 - bitlen((unsigned)lps);     // renorm table, HEVCe.c:715
+        const bool is_lps = ((v ^ bin) & 1) != 0;                   // bin is 0 or 1 at every call site
+        // renorm table, HEVCe.c:715: 9 - bitlen(lps) for lps >= 6; the only smaller entry (2, probability state 63) cannot
+        // be reached: contexts are initialised to states 1..126 (ctx_init_value) and the MPS transition stops at 62
+        const int nb = 9 - bitlen((unsigned)lps);
+#if !defined(__CUDA_ARCH__)
+        if (v >= 126 || (unsigned)bin > 1u) __builtin_trap();
+#endif
         const int sh = is_lps ? nb : (rmps < 256 ? 1 : 0);
         c.low = (int)((unsigned)(is_lps ? c.low + rmps : c.low) << sh);
         c.range = (is_lps ? lps : rmps) << sh;
@@ -383,6 +472,7 @@ struct BacT {
             cx = (u8)(v < 124 ? v + 2 : v);
             if (c.range < 256) { c.low = (int)((unsigned)c.low << 1); c.range <<= 1; c.nbits--; }
         }
+#endif
 #endif
         carry_out();
     }
@@ -415,13 +505,12 @@ struct BacT {
 typedef BacT<false> Bac;        // trial coder: full integer state, no byte store
 typedef BacT<true> BacCommit;   // commit coder: writes the CTU's bytes
 
-// context set: byte k at base[(k>>2)*s4 + (k&3)].  s4 = 4: plain array; s4 = 4*NLANE: lane-private column of the
-// word-interleaved shared-memory array (every lane owns one bank).  The base pointer is always derived from the
-// picture's shared-memory block inside the function that uses it, so the accesses stay LDS/STS.
+// context set: 4 * CTXW contiguous bytes (lane-major in the shared-memory array of lane-private sets: CTXW is odd, so
+// the sets of 32 consecutive lanes start in 32 different banks).  The base pointer is always derived from the picture's
+// shared-memory block inside the function that uses it, so the accesses stay LDS/STS.
 struct Cx {
     u8* p;
-    int s4;
-    HEVCE_HD u8& operator[](int k) const { return p[(k >> 2) * s4 + (k & 3)]; }
+    HEVCE_HD u8& operator[](int k) const { return p[k]; }
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -522,7 +611,7 @@ constexpr int AUX_CODER = POOL_BYTES - 1984;       // pool tail: trial-coder res
 struct Shared {
     // (field order as measured: moving the candidate arrays in front of the picture state cost the 7-picture variant 3 %)
     alignas(16) u8 pool[POOL_BYTES];    // per-node carve-up: work blocks, predictions, borders (see Plan<S>)        [track]
-    u32 lane_ctx[CTXW * NLANE];         // lane-private context sets, word-interleaved                               [track]
+    u32 lane_ctx[NLANE * CTXW];         // lane-private context sets, lane-major (set L at word L * CTXW)            [track]
     // ---- the picture's state: owned by track 0; the cluster variant pushes [ctx0, ctu_lev) and q into the parent tracks' blocks
     alignas(16) u8 ctx0[4 * CTXW];      // freshly initialised contexts for this picture's qpd6
     alignas(16) u8 live_ctx[4 * CTXW];
@@ -867,7 +956,7 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
         const int row = lg - 2, sh = s > 4;
         int ty = st == 2 ? x : y, tx = st == 2 ? y : x;
         const int gy = tb->grp[ty], gx = tb->grp[tx], gmax = tb->grp[s - 1];
-        const int bx = CX_LASTX + 5 * row, by = CX_LASTY + 5 * row;
+        const int bx = cx_lastx(row), by = cx_lasty(row);
         for (int i = 0; i < gx; i++) b.put_bin(tbl, 1, cx[bx + (i >> sh)]);
         if (gx < gmax) b.put_bin(tbl, 0, cx[bx + (gx >> sh)]);
         for (int i = 0; i < gy; i++) b.put_bin(tbl, 1, cx[by + (i >> sh)]);
@@ -884,17 +973,16 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
     }
     // ---- sig_coeff_flags (HEVCe.c:1219-1222, context HEVCe.c:1092-1122)
     {
-        const u32 soff = tb->sigoff[st][pat];
-        const unsigned long long s4 = tb->sig4[st];
-        const int base = sigbase + (first_cg ? 0 : 3);
+        // one 4-bit field per scan index: the context of a 4x4 TU's position, or the neighbour-pattern offset of a larger TU
+        const unsigned long long tab = s == 4 ? tb->sig4[st] : tb->sigoff[st][pat];
+        const int base = s == 4 ? CX_SIG : sigbase + (first_cg ? 0 : 3);
+        const bool dc = first_cg && s != 4;                         // position 0 of a larger TU has its own context
         int k = is_last ? kstart - 1 : 15;
         const int kend = (!first_cg && (nzm & ~1u) == 0) ? 1 : 0;   // position 0 of a later group is inferred when it is the only one
         for (; k >= kend; k--) {
-            int ci;
-            if (s == 4) ci = CX_SIG + (int)((s4 >> (4 * k)) & 15u);
-            else if (first_cg && k == 0) ci = CX_SIG;
-            else ci = base + (int)((soff >> (2 * k)) & 3u);
-            b.put_bin(tbl, (nzm >> k) & 1u, cx[ci]);
+            int ci = base + (int)((tab >> (4 * k)) & 15u);
+            if (dc && k == 0) ci = CX_SIG;
+            b.put_bin(tbl, (int)((nzm >> k) & 1u), cx[ci]);
         }
     }
     if (nzm) {
@@ -1039,7 +1127,7 @@ HEVCE_HD inline void put_residual(BAC& b, const Tables& tbl, const Cx cx, int s,
 // in its own small shared block.  Both are reached through the extern shared array so the accesses stay LDS/STS.
 struct CommitShared {
     Tables tb;
-    u32 ctx[CTXW * NTC];  // lane-private context sets of the NTC commit threads of a block, word-interleaved
+    u32 ctx[NTC * CTXW];  // lane-private context sets of the NTC commit threads of a block, lane-major
 };
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ CommitShared& my_csm() { return *reinterpret_cast<CommitShared*>(hevce_smem); }
@@ -1070,10 +1158,11 @@ struct CuDesc {
 };
 
 template <class BAC, class ENV>
-HEVCE_HD HEVCE_NOINLINE void code_cu(BAC& bio, int pic, int cx_off, int cx_s4, const CuDesc& d) {
+HEVCE_HD HEVCE_NOINLINE void code_cu(BAC& bio, int pic, int cx_off, const CuDesc& d) {
     const Tables& tbl = ENV::tables();
-    const Cx cx = {ENV::base(pic) + cx_off, cx_s4};
+    const Cx cx = {ENV::base(pic) + cx_off};
     BAC b = bio;   // coder state in registers for the whole CU
+    b.use_tables(tbl);
     const int s = d.s, kind = d.kind;
     if (kind != 3) {
         if (d.split_ctx >= 0 && s >= 16) b.put_bin(tbl, 0, cx[CX_SPLIT_CU + d.split_ctx]);
@@ -1297,10 +1386,56 @@ HEVCE_HD inline void phase_a_item(Shared& sm, const Shared& pm, const Grp& g, in
     for (int k = 0; k < T; k++) bp[k * T] = (s16)((o[k] + (1 << A1 >> 1)) >> A1);
 }
 
+// Per-coefficient RDOQ (HEVCe.c:563-586): the level of coefficient cf, unsigned; dl receives |cf| << 14 for the group sums.
+// RD cost without the saturation tests of HEVCe.c:182-184: here dist <= 2^24 and rate <= 1.2e6, so neither product nor
+// the sum can reach 2^31 and the plain weighted sum is the same number.
+struct RdoqK { int dsh, sh, add, wd, wb; };
+HEVCE_HD inline RdoqK rdoq_consts(int lg, int q) {
+    const RdK rk = rd_consts(q);
+    RdoqK k;
+    k.dsh = 10 - lg; k.sh = 21 - lg + q; k.add = 1 << k.sh >> 1; k.wd = rk.wd; k.wb = rk.wb;
+    return k;
+}
+HEVCE_HD inline int rdoq_level(int cf, const RdoqK& k, const Tables& tb, int& dl) {
+    dl = iabs(cf) << 14;                                         // |cf| <= 32767: the clamps of HEVCe.c:566 cannot trigger
+    const int lvl = (dl + k.add) >> k.sh;
+    if (lvl <= 0) return 0;
+#if HEVCE_OPT_RDOQ2
+    // Candidates lvl and lvl-1 only: the third one of HEVCe.c:571, lvl-2, can never be picked.  One level is
+    // U = 2^(11+q) in units of the distance e; e(lvl) <= U/2, e(lvl-1) = a in [U/2, 3U/2), e(lvl-2) = a + U exactly
+    // (2^sh is a multiple of 2^dsh).  qpd6 <= 3: nothing saturates (5U/2 < 46340) and dist(lvl-2) - dist(lvl-1) >=
+    // U^2/64 - 1 = 2^(16+2q) - 1; times wd = 11/11/11/5 that is >= 720,885 / 2.9 M / 11.5 M / 21 M against at most
+    // wb * 70,000 = 70,000 / 280,000 / 1.12 M / 2.03 M of rate (70,000 is the largest step between neighbouring
+    // levels): lvl-1 is strictly cheaper than lvl-2.  qpd6 = 4: dist(lvl-2) saturates to 2^24 - 1 while dist(lvl) <=
+    // 2^21, and two levels are worth at most 23 * 131,072 = 3.0 M of rate: lvl is strictly cheaper than lvl-2.
+    // The scan keeps the higher level on a tie, so lvl-1 wins iff cost(lvl-1) < cost(lvl), i.e. iff
+    // wd * (dist(lvl-1) - dist(lvl)) < wb * (rate(lvl) - rate(lvl-1)); the rate step comes from an 8-entry table
+    // (HEVCe.c:526-535: from level 7 on it is 65536 when lvl-5 is a power of two, else 0).  No product reaches 2^31.
+    // tests/test_stages.py: every |cf| x TU size x qpd6 against the reference's quantize().
+    const int e0 = iabs(dl - (lvl << k.sh)) >> k.dsh;
+    const int e1 = (dl - ((lvl - 1) << k.sh)) >> k.dsh;
+    const int d0 = (e0 * e0) >> 7;
+    const int d1 = (e1 < 46340 ? e1 * e1 : IMAX) >> 7;          // saturates at qpd6 = 4 only
+    const int dr = tb.drate[imin(lvl, 7)] + ((lvl >= 7 && ((lvl - 5) & (lvl - 6)) == 0) ? 65536 : 0);
+    return k.wd * (d1 - d0) < k.wb * dr ? lvl - 1 : lvl;
+#else
+    // candidates lvl, lvl-1, lvl-2 (>= 0); strict '<' scanning downwards: the highest level wins ties
+    int pick = lvl, best = IMAX;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        const int l = lvl - t;
+        const int d1 = iabs(dl - (l << k.sh)) >> k.dsh;
+        const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
+        const int wr = k.wb * (l < 32 ? tb.rate32[imax(l, 0)] : 92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15));   // HEVCe.c:526-535
+        const int cost = k.wd * d + wr;
+        if (l >= 0 && cost < best) { best = cost; pick = l; }
+    }
+    return pick;
+#endif
+}
+
 // phase B: forward row transform (HEVCe.c:515) + per-coefficient RDOQ (HEVCe.c:563-586); tentative levels replace
 // the coefficients in place, the clamped magnitudes are summed per (row, group column) for the zero-out test.
-// RD cost without the saturation tests of HEVCe.c:182-184: here dist <= 2^24 and rate <= 1.1e6, so neither product
-// nor the sum can reach 2^31 and the plain weighted sum is the same number.
 template <int T>
 HEVCE_HD inline void phase_b_item(Shared& sm, const Shared& pm, const Grp& g, int item, int q, const RdK& rk) {
     constexpr int LG = Dim<T>::LG, BLK = Dim<T>::BLK, A2 = LG + 6;
@@ -1314,9 +1449,9 @@ HEVCE_HD inline void phase_b_item(Shared& sm, const Shared& pm, const Grp& g, in
 #pragma unroll
         for (int x = 0; x < T; x++) bp[x] = (s16)((o[x] + (1 << A2 >> 1)) >> A2);
     }
-    const int dsh = 10 - LG, sh = 21 - LG + q, add = 1 << sh >> 1, thr = 9 << sh >> 2;
-    const int wd = rk.wd, wb = rk.wb;
-    const int* rate32 = my_tb().rate32;
+    const RdoqK k = rdoq_consts(LG, q);
+    const int thr = 9 << k.sh >> 2;
+    const Tables& tb = my_tb();
     int* ps = (int*)(sm.pool + g.psum) + c * (T * T / 4) + y * (T / 4);
 #pragma unroll 1
     for (int gx = 0; gx < T / 4; gx++) {
@@ -1325,21 +1460,9 @@ HEVCE_HD inline void phase_b_item(Shared& sm, const Shared& pm, const Grp& g, in
         for (int e = 0; e < 4; e++) {
             const int x = gx * 4 + e;
             const int cf = bp[x];
-            const int dl = iabs(cf) << 14;                       // |cf| <= 32640: the clamps of HEVCe.c:566 cannot trigger
-            const int lvl = (dl + add) >> sh;
-            if (lvl > 0) {   // candidates lvl, lvl-1, lvl-2 (>= 0); strict '<' scanning downwards: the highest level wins ties
-                int pick = lvl, best = IMAX;
-#pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    const int l = lvl - t;
-                    const int d1 = iabs(dl - (l << sh)) >> dsh;
-                    const int d = (d1 < 46340 ? d1 * d1 : IMAX) >> 7;
-                    const int wr = wb * (l < 32 ? rate32[imax(l, 0)] : 92000 + ((4 + 2 * (bitlen((unsigned)(l - 5)) - 1)) << 15));   // HEVCe.c:526-535
-                    const int cost = wd * d + wr;
-                    if (l >= 0 && cost < best) { best = cost; pick = l; }
-                }
-                bp[x] = (s16)(cf < 0 ? -pick : pick);
-            } else bp[x] = 0;
+            int dl;
+            const int pick = rdoq_level(cf, k, tb, dl);
+            bp[x] = (s16)(cf < 0 ? -pick : pick);
             sum += imin(dl, thr);
         }
         ps[gx] = sum;
@@ -1540,6 +1663,7 @@ template <int S> struct Plan {
 HEVCE_HD inline Bac make_bac(const Coder& c) {
     Bac b;
     b.c = c; b.out = nullptr; b.cap = 0;
+    b.use_tables(my_tb());
     return b;
 }
 HEVCE_HD inline int sm_off(const Shared& sm, const void* p) { return (int)((const u8*)p - (const u8*)&sm); }
@@ -1561,17 +1685,15 @@ HEVCE_HD inline void trial_lane(int pic, int trk, int cand, int depth, int y0, i
     Bac b = make_bac(pm.snap[depth]);
     if (pu) coder_reset(b.c);
     const int base_len = pu ? coder_len(b.c) : coder_len(pm.snap[depth]);
-    if (pu) {   // a 4x4 luma TU touches last_x/y row 0 (words 4, 9), sig 0..8 (14-16), greater1 0..15 (21-24), greater2 0..3 (25)
+    u32* lane_cx = sm.lane_ctx + slot * CTXW;
+    if (pu) {   // everything the residual of a 4x4 luma TU touches sits in the first CTXW4 words (see the layout at CX_LASTX4)
         const u32* src = (const u32*)pm.ctx0;
-        u32* dst = sm.lane_ctx + slot;
-        const int W4[10] = {4, 9, 14, 15, 16, 21, 22, 23, 24, 25};
 #pragma unroll
-        for (int k = 0; k < 10; k++) dst[W4[k] * NLANE] = src[W4[k]];
+        for (int k = 0; k < CTXW4; k++) lane_cx[k] = src[k];
     } else {
         const u32* src = (const u32*)pm.snap_ctx[depth];
-        u32* dst = sm.lane_ctx + slot;
-#pragma unroll 4
-        for (int k = 0; k < CTXW; k++) dst[k * NLANE] = src[k];
+#pragma unroll
+        for (int k = 0; k < CTXW; k++) lane_cx[k] = src[k];
     }
     CuDesc d;
     d.s = S; d.kind = pu ? 3 : step; d.split_ctx = split_ctx;
@@ -1583,7 +1705,7 @@ HEVCE_HD inline void trial_lane(int pic, int trk, int cand, int depth, int y0, i
     } else {
         d.lev[0] = lev; d.mlo[0] = sm.cgnz[cand][0]; d.mhi = pu ? 0u : sm.cgnz[cand][1];
     }
-    code_cu<Bac, MainEnv>(b, local_block(pic, trk), sm_off(sm, sm.lane_ctx + slot), 4 * NLANE, d);
+    code_cu<Bac, MainEnv>(b, local_block(pic, trk), sm_off(sm, lane_cx), d);
     const int bits = coder_len(b.c) - base_len;
     if (pu) sm.cand_bits[cand] = bits;
     else {   // the lane leaves its RD cost (the distortion is complete since phase D) and its end state
@@ -1605,7 +1727,7 @@ HEVCE_HD inline void nxn_trial(Shared& sm, int pic, int depth, int y0, int x0) {
     d.pl[1] = d.pm[0]; d.pa[1] = sm.mpm[(my - 1) * 9 + mx + 1];
     d.pl[2] = sm.mpm[(my + 1) * 9 + mx - 1]; d.pa[2] = d.pm[0];
     d.pl[3] = d.pm[2]; d.pa[3] = d.pm[1];
-    code_cu<Bac, MainEnv>(b, local_block(pic, 0), sm_off(sm, sm.nxn_ctx), 4, d);
+    code_cu<Bac, MainEnv>(b, local_block(pic, 0), sm_off(sm, sm.nxn_ctx), d);
     int sse = 0;
     for (int y = 0; y < 8; y++)
         for (int x = 0; x < 8; x++) { const int dd = (int)sm.orig[(y0 + y) * CTU + x0 + x] - HEVCE_WIN(sm, y0 + y, x0 + x); sse += dd * dd; }
@@ -1837,7 +1959,7 @@ HEVCE_HD HEVCE_NOINLINE void decide_adopt(int q, int y0, int x0, int depth) {
             HEVCE_WIN(sm, y0 + i / S, x0 + i % S) = rp[i];
             clev[i] = lp[i];
         }
-        PAR_FOR(i, CTXW) ((u32*)sm.live_ctx)[i] = cm.lane_ctx[i * NLANE + win];
+        PAR_FOR(i, CTXW) ((u32*)sm.live_ctx)[i] = cm.lane_ctx[win * CTXW + i];
         PAR_FOR(i, N4 * N4) {
             const int idx = (my + i / N4) * 9 + mx + i % N4;
             sm.msz[idx] = (u8)S;
@@ -1869,7 +1991,7 @@ HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
         PAR_FOR(one, 1) {
             const int my = 1 + y0 / 4, mx = 1 + x0 / 4;
             Bac b = make_bac(sm.live);
-            const Cx cx = {sm.live_ctx, 4};
+            const Cx cx = {sm.live_ctx};
             b.put_bin(my_tb(), 1, cx[CX_SPLIT_CU + (S > sm.msz[my * 9 + mx - 1]) + (S > sm.msz[(my - 1) * 9 + mx])]);   // HEVCe.c:943-947
             sm.live = b.c;
         }
@@ -1880,7 +2002,7 @@ HEVCE_HD inline void enter_node(Shared& sm, int y0, int x0, int depth) {
 // Commit pass: re-encode one decided CTU with the byte-writing coder from its recorded start state (replaces the
 // reference's per-trial byte buffers).  One thread per CTU in hevce_commit_kernel; CTUs are independent here because
 // the decision kernel recorded every CTU's start state and byte offset.
-HEVCE_HD inline void commit_cu(BacCommit& b, int cx_off, int cx_s4, const CtuRec& r, const s16* ctu_lev, int s, int y0, int x0) {
+HEVCE_HD inline void commit_cu(BacCommit& b, int cx_off, const CtuRec& r, const s16* ctu_lev, int s, int y0, int x0) {
     const int my = 1 + y0 / 4, mx = 1 + x0 / 4, h = s / 2;
     CuDesc d;
     d.s = s; d.kind = r.kind[(y0 >> 3) * 4 + (x0 >> 3)]; d.split_ctx = -1; d.mhi = 0;
@@ -1897,25 +2019,26 @@ HEVCE_HD inline void commit_cu(BacCommit& b, int cx_off, int cx_s4, const CtuRec
     if (d.kind == 0) { d.lev[0] = lev; scan_groups(lev, s, d.mlo[0], d.mhi); }
     else
         for (int k = 0; k < 4; k++) { unsigned hi; d.lev[k] = lev + k * h * h; scan_groups(d.lev[k], h, d.mlo[k], hi); }
-    code_cu<BacCommit, CommitEnv>(b, 0, cx_off, cx_s4, d);
+    code_cu<BacCommit, CommitEnv>(b, 0, cx_off, d);
 }
 
 HEVCE_HD inline void commit_ctu(const Job& job, int ctu, int lane) {
     CommitShared& cs = my_csm();
     const CtuRec& r = job.recs[ctu];
     const s16* lev = job.levs + (size_t)ctu * (CTU * CTU);
-    u32* cw = cs.ctx + lane;
-    for (int k = 0; k < CTXW; k++) cw[k * NTC] = ((const u32*)r.ctx)[k];
-    const int cx_off = (int)((u8*)cw - (u8*)&cs), cx_s4 = 4 * NTC;
-    const Cx cx = {(u8*)cw, cx_s4};
+    u32* cw = cs.ctx + lane * CTXW;
+    for (int k = 0; k < CTXW; k++) cw[k] = ((const u32*)r.ctx)[k];
+    const int cx_off = (int)((u8*)cw - (u8*)&cs);
+    const Cx cx = {(u8*)cw};
     BacCommit b;
+    b.use_tables(cs.tb);
     b.c = r.start;
     b.out = job.out + r.out_pos;
     b.cap = imax(0, job.out_cap - r.out_pos);
     auto gt = [&](int s, int y, int x) { return (s > r.msz[(1 + y / 4) * 9 + 1 + x / 4 - 1]) + (s > r.msz[(1 + y / 4 - 1) * 9 + 1 + x / 4]); };
     const int whole = r.msz[10] == 32;
     b.put_bin(cs.tb, !whole, cx[CX_SPLIT_CU + gt(32, 0, 0)]);
-    if (whole) commit_cu(b, cx_off, cx_s4, r, lev, 32, 0, 0);
+    if (whole) commit_cu(b, cx_off, r, lev, 32, 0, 0);
     else
         for (int a = 0; a < 4; a++) {
             const int y16 = (a >> 1) * 16, x16 = (a & 1) * 16;
@@ -1923,8 +2046,8 @@ HEVCE_HD inline void commit_ctu(const Job& job, int ctu, int lane) {
             b.put_bin(cs.tb, sz != 16, cx[CX_SPLIT_CU + gt(16, y16, x16)]);
             const int ncu = sz == 16 ? 1 : 4;
             for (int c = 0; c < ncu; c++) {
-                if (sz == 16) commit_cu(b, cx_off, cx_s4, r, lev, 16, y16, x16);
-                else commit_cu(b, cx_off, cx_s4, r, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
+                if (sz == 16) commit_cu(b, cx_off, r, lev, 16, y16, x16);
+                else commit_cu(b, cx_off, r, lev, 8, y16 + (c >> 1) * 8, x16 + (c & 1) * 8);
             }
         }
     b.put_terminate(r.last);   // HEVCe.c:1630
@@ -1933,7 +2056,7 @@ HEVCE_HD inline void commit_ctu(const Job& job, int ctu, int lane) {
     if (!coder_equal(b.c, r.end)) err |= ERR_COMMIT_MISMATCH;   // the adopted trial state must be what the bytes produce
     if (!r.last) {
         const u32* nx = (const u32*)job.recs[ctu + 1].ctx;
-        for (int k = 0; k < CTXW; k++) if (cw[k * NTC] != nx[k]) err |= ERR_COMMIT_MISMATCH;
+        for (int k = 0; k < CTXW; k++) if (cw[k] != nx[k]) err |= ERR_COMMIT_MISMATCH;
     }
     if (b.c.n > b.cap) err |= ERR_OVERFLOW;
     if (err) HEVCE_ATOMIC_OR(job.result + 1, err);

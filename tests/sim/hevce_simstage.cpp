@@ -4,6 +4,7 @@
 //   hevce_stage_pixel    : reference samples -> prediction -> residual -> forward transform -> RDOQ -> group zero-out ->
 //                          dequantisation -> inverse transform -> reconstruction + SSE of ONE candidate (phases border, A-D)
 //   hevce_stage_residual : residual_coding() of one TU from a fresh coder and fresh contexts (put_residual)
+//   hevce_stage_rdoq     : the per-coefficient RDOQ decision (rdoq_level) for a list of coefficients
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -75,6 +76,17 @@ extern "C" int hevce_stage_pixel(int T, int mode, int q, const unsigned char* wi
     return 0;
 }
 
+// The level RDOQ picks for each of n coefficients of a TU of size T at qpd6 = q (before the coefficient-group zero-out).
+extern "C" void hevce_stage_rdoq(int T, int q, int n, const int* cf, int* lev) {
+    const Tables& tb = *tables();
+    const RdoqK k = rdoq_consts(ilog2(T), q);
+    for (int i = 0; i < n; i++) {
+        int dl;
+        const int pick = rdoq_level(cf[i], k, tb, dl);
+        lev[i] = cf[i] < 0 ? -pick : pick;
+    }
+}
+
 // lev: T*T raster levels.  state: {range, low, nbits, nbytes, held, z, n} at the end.  returns the bits written.
 extern "C" int hevce_stage_residual(int T, int mode, int q, const int* lev, int* state) {
     const Tables& tb = *tables();
@@ -94,9 +106,9 @@ extern "C" int hevce_stage_residual(int T, int mode, int q, const int* lev, int*
             }
     Bac b;
     coder_reset(b.c);
-    b.out = nullptr; b.cap = 0;
+    b.out = nullptr; b.cap = 0; b.tabs = 0;
     const int len0 = coder_len(b.c);
-    const Cx cx = {ctx, 4};
+    const Cx cx = {ctx};
     put_residual(b, tb, cx, T, mode, blocked.data(), mlo, mhi);
     state[0] = b.c.range; state[1] = b.c.low; state[2] = b.c.nbits; state[3] = b.c.nbytes; state[4] = b.c.held; state[5] = b.c.z; state[6] = b.c.n;
     return coder_len(b.c) - len0;
@@ -122,6 +134,7 @@ extern "C" int hevce_stage_bypass_grouping(unsigned seed, int nitems, int* len) 
         for (int i = 0; i < 4 * CTXW; i++) ctx[i] = ctx_init_value(tb.ctx_iv[i], 2);
         out[pass].assign((size_t)nitems * 8 + 64, 0);
         BacCommit b;
+        b.tabs = 0;
         coder_reset(b.c);
         b.out = out[pass].data(); b.cap = (int)out[pass].size();
         unsigned s2 = seed ^ 0x9e3779b9u;

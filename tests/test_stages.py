@@ -120,6 +120,34 @@ def test_pixel_stages_match_reference_functions(libs, T):
     assert n == 175
 
 
+@pytest.mark.parametrize("T", [4, 8, 16, 32])
+def test_rdoq_every_coefficient_value(libs, T):
+    """The per-coefficient RDOQ decision for EVERY coefficient value -32767..32767, every TU size and qpd6, against the
+    reference's quantize() (HEVCe.c:540).  The kernel evaluates two candidate levels through a rate-step table where the
+    reference scans three with calcRDcost; this is the exhaustive check of that shortcut.  Every coefficient group of the
+    reference's input carries one large guard value so that the group zero-out (HEVCe.c:589) never clears the group."""
+    ours, ref = libs
+    vals = np.concatenate([np.arange(0, 32768), -np.arange(1, 32768)]).astype(np.int32)
+    ncg = (T // 4) ** 2
+    per_block = 15 * ncg
+    pad = (-len(vals)) % per_block
+    vals = np.concatenate([vals, np.zeros(pad, np.int32)])
+    slots = [(4 * gy + r, 4 * gx + c) for gy in range(T // 4) for gx in range(T // 4) for r in range(4) for c in range(4) if (r, c) != (0, 0)]
+    ys, xs = np.array([s[0] for s in slots]), np.array([s[1] for s in slots])
+    for q in range(5):
+        got = np.zeros(len(vals), np.int32)
+        ours.hevce_stage_rdoq(T, q, len(vals), vals.ctypes.data_as(_ip), got.ctypes.data_as(_ip))
+        want = np.zeros(len(vals), np.int32)
+        for b in range(len(vals) // per_block):
+            coef, lev = np.zeros((32, 32), np.int32), np.zeros((32, 32), np.int32)
+            coef[0:T:4, 0:T:4] = 32767                                            # the guards
+            coef[ys, xs] = vals[b * per_block:(b + 1) * per_block]
+            ref.quantize(q, T, 0, coef.ctypes.data_as(_ip), lev.ctypes.data_as(_ip))
+            want[b * per_block:(b + 1) * per_block] = lev[ys, xs]
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (T, q, int(vals[bad[0]]), int(got[bad[0]]), int(want[bad[0]]))
+
+
 def ref_residual(ref, T, mode, q, lev):
     cab, ctx = ref.newCABACcoder(), ref.newContextSet(q)
     blk = np.zeros((32, 32), np.int32)
