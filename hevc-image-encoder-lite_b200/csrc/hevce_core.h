@@ -67,8 +67,17 @@
 #endif
 // put_bin: one 32-bit table word per (context state, range quarter) carrying the LPS range, the LPS renormalisation
 // shift and both next states (one shared-memory load per bin instead of two or three plus the shift arithmetic)
+// 1: word per (state, range quarter), plain load; 2: the same through an explicit ld.shared (no re-derived window base);
+// 3: one 64-bit word per state (the four LPS ranges + both next states) loaded as soon as the context byte is known: the
+//    load no longer waits for the previous bin's range, which leaves the range recurrence shift -> byte select -> subtract ->
+//    compare -> select -> shift, all register arithmetic
 #ifndef HEVCE_OPT_BINTAB
-#define HEVCE_OPT_BINTAB 1
+#define HEVCE_OPT_BINTAB 3
+#endif
+// consecutive bins of a loop that hit the same context take its state from a register instead of reading back the byte
+// they have just stored
+#ifndef HEVCE_OPT_CTXFWD
+#define HEVCE_OPT_CTXFWD 0
 #endif
 // Trial coder, byte release: the common case (exactly one pending byte, the new lead byte is not 0xFF, the released byte is
 // above 3 so neither an emulation-prevention byte nor a zero run is involved) as predicated straight-line code on every
@@ -76,6 +85,13 @@
 // version is paid in full almost every time.
 #ifndef HEVCE_OPT_RELPRED
 #define HEVCE_OPT_RELPRED 0
+#endif
+// bit-fields of a coefficient group built two levels at a time (signs gathered by shift + mask, the non-zero mask squeezed
+// out of the class field) instead of level by level: 100 instead of 159 instructions per group.  Measured (profiles/
+// r2_ab_fastbuild_*.log): -0.7 % on the one-picture-per-CTA cluster variant, +0.6 % on the 7-picture gang, where the longer
+// live ranges cost spills at the 72-register cap -- so it is on for the variants with one picture per CTA only.
+#ifndef HEVCE_OPT_FASTBUILD
+#define HEVCE_OPT_FASTBUILD (HEVCE_OPT_GANG == 1)
 #endif
 // RDOQ evaluates the two candidate levels that can win (proof at phase_b_item); 0 = all three of HEVCe.c:571
 #ifndef HEVCE_OPT_RDOQ2
@@ -188,6 +204,7 @@ HEVCE_HD inline int bitlen(unsigned v) {
 struct Tables {
     u32 lps4[64];          // rangeTabLps, one word per state: byte q = LPS range for (range>>6)&3 == q  (HEVCe.c:704-713)
     u8 next_lps[128];      // (state<<1|mps) after an LPS                   (HEVCe.c:702)
+    unsigned long long st8[128];   // per ctx = state<<1|mps: bytes 0..3 LPS range by range quarter, byte 4 ctx after an LPS, byte 5 after an MPS
     u32 bin4[4 + 512];     // [4 + ctx*4 + q], ctx = state<<1|mps, q = (range>>6)&3 (range>>6 is 4..7, hence the 4 unused words in front):
                            // byte 0 LPS range, byte 1 ctx after an LPS, byte 2 ctx after an MPS, bits 29..31 LPS renorm shift (HEVCe.c:701-715)
     u8 ctx_iv[4 * CTXW];   // context init values by (compact) context index    (HEVCe.c:763-777)
@@ -232,6 +249,10 @@ inline void fill_tables(Tables& t) {
     for (int s = 0; s < 64; s++) t.lps4[s] = (u32)LPS[s][0] | ((u32)LPS[s][1] << 8) | ((u32)LPS[s][2] << 16) | ((u32)LPS[s][3] << 24);
     for (int s = 0; s < 64; s++)
         for (int m = 0; m < 2; m++) t.next_lps[(s << 1) | m] = (u8)((TRANS_LPS[s] << 1) | (s == 0 ? !m : m));
+    for (int v = 0; v < 128; v++) {
+        const unsigned long long nmps = v < 124 ? v + 2 : v;
+        t.st8[v] = (unsigned long long)t.lps4[v >> 1] | ((unsigned long long)t.next_lps[v] << 32) | (nmps << 40);
+    }
     for (int i = 0; i < 4; i++) t.bin4[i] = 0;
     for (int v = 0; v < 128; v++)
         for (int q = 0; q < 4; q++) {
@@ -334,8 +355,8 @@ struct BacT {
     // The bin table is read with an explicit ld.shared from an address the compiler cannot re-derive: left to itself it
     // rebuilds the shared-window base (S2UR + UMOV + ULEA) in front of every bin.
     HEVCE_HD void use_tables(const Tables& tb) {
-#if defined(__CUDA_ARCH__) && HEVCE_OPT_BINTAB == 2
-        tabs = (u32)__cvta_generic_to_shared(&tb.bin4[0]);
+#if defined(__CUDA_ARCH__) && HEVCE_OPT_BINTAB >= 2
+        tabs = HEVCE_OPT_BINTAB == 2 ? (u32)__cvta_generic_to_shared(&tb.bin4[0]) : (u32)__cvta_generic_to_shared(&tb.st8[0]);
         asm volatile("mov.u32 %0, %0;" : "+r"(tabs));
 #else
         (void)tb; tabs = 0;
@@ -416,9 +437,37 @@ struct BacT {
             c.nbytes = ff ? c.nbytes + 1 : 1;
         }
     }
-    HEVCE_HD void put_bin(const Tables& tb, int bin, u8& cx) {   // HEVCe.c:914-933, both branches computed, then selected
-        const int v = cx;
-#if HEVCE_OPT_BINTAB
+    HEVCE_HD void put_bin(const Tables& tb, int bin, u8& cx) { cx = (u8)bin_step(tb, bin, cx); }
+    // one context-coded bin with context byte v; returns the new context byte (HEVCe.c:914-933, both branches computed, then selected)
+    HEVCE_HD int bin_step(const Tables& tb, int bin, const int v) {
+        int cxn;
+#if HEVCE_OPT_BINTAB == 3
+#if defined(__CUDA_ARCH__)
+        u32 lo, hi;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(tabs + (u32)v * 8u));
+        // range >> 6 is 4..7: byte 0..3 of lo; the other selector nibbles are 0 and pick byte 0 of the zero operand.  Raw prmt:
+        // __byte_perm first masks the selector (one more instruction on the range -> range recurrence).
+        u32 lps_u;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(lps_u) : "r"(0u), "r"(lo), "r"((u32)c.range >> 6));
+        const int lps = (int)lps_u;
+#else
+        const u32 lo = (u32)tb.st8[v], hi = (u32)(tb.st8[v] >> 32);
+        const int lps = (int)((lo >> (8 * ((c.range >> 6) & 3))) & 0xffu);
+#endif
+        const int rmps = c.range - lps;
+        const bool is_lps = ((v ^ bin) & 1) != 0;                   // bin is 0 or 1 at every call site
+        // renorm table, HEVCe.c:715: 9 - bitlen(lps) for lps >= 6; the only smaller entry (2, probability state 63) cannot
+        // be reached: contexts are initialised to states 1..126 (ctx_init_value) and the MPS transition stops at 62
+        const int sh = is_lps ? 9 - bitlen((unsigned)lps) : (rmps < 256 ? 1 : 0);
+        if (is_lps) c.low += rmps;
+        c.low = (int)((unsigned)c.low << sh);
+        c.range = (is_lps ? lps : rmps) << sh;
+        c.nbits -= sh;
+        cxn = (int)((is_lps ? hi : hi >> 8) & 0xffu);
+#if !defined(__CUDA_ARCH__)
+        if (v >= 126 || (unsigned)bin > 1u || c.range < 256 || c.range > 510) __builtin_trap();
+#endif
+#elif HEVCE_OPT_BINTAB
 #if defined(__CUDA_ARCH__) && HEVCE_OPT_BINTAB == 2
         u32 w;
         asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(tabs + (u32)(v * 4 + (c.range >> 6)) * 4u));
@@ -435,7 +484,7 @@ struct BacT {
         c.nbits -= sh;
         u32 nx = w >> 8;
         if (!is_lps) nx >>= 8;
-        cx = (u8)nx;
+        cxn = (int)(nx & 0xffu);
 #if !defined(__CUDA_ARCH__)
         if ((unsigned)bin > 1u || c.range < 256 || c.range > 510) __builtin_trap();
 #endif
@@ -459,22 +508,23 @@ struct BacT {
         c.low = (int)((unsigned)(is_lps ? c.low + rmps : c.low) << sh);
         c.range = (is_lps ? lps : rmps) << sh;
         c.nbits -= sh;
-        cx = (u8)(is_lps ? nlps : (v < 124 ? v + 2 : v));           // HEVCe.c:701-702
+        cxn = is_lps ? nlps : (v < 124 ? v + 2 : v);                // HEVCe.c:701-702
 #else
         c.range -= lps;
         if ((bin != 0) != ((v & 1) != 0)) {
             const int nb = lps < 8 ? 6 : 9 - bitlen((unsigned)lps);
-            cx = tb.next_lps[v];
+            cxn = tb.next_lps[v];
             c.low = (int)((unsigned)(c.low + c.range) << nb);
             c.range = lps << nb;
             c.nbits -= nb;
         } else {
-            cx = (u8)(v < 124 ? v + 2 : v);
+            cxn = v < 124 ? v + 2 : v;
             if (c.range < 256) { c.low = (int)((unsigned)c.low << 1); c.range <<= 1; c.nbits--; }
         }
 #endif
 #endif
         carry_out();
+        return cxn;
     }
     HEVCE_HD void put_bypass(int bins, int len) {   // HEVCe.c:899-911
         bins &= (1 << len) - 1;
@@ -937,6 +987,7 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
     const Tables* tb = &tbl;
     // ---- bit-fields of the group, scan order
     unsigned nzm = 0, sgn = 0, cls = 0;
+#if !HEVCE_OPT_FASTBUILD
     if (on) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
@@ -947,6 +998,23 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
             cls |= a << (2 * k);
         }
     }
+#else
+    if (on) {   // word j holds the levels of scan positions 2j (low half) and 2j+1
+        unsigned sg = 0;   // sign of position 2j at bit 2j, of position 2j+1 at bit 16+2j
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            sg |= (w[j] >> (15 - 2 * j)) & (0x00010001u << (2 * j));
+            const unsigned a0 = (unsigned)imin(iabs((int)(s16)w[j]), 3), a1 = (unsigned)imin(iabs((int)w[j] >> 16), 3);
+            cls |= (a0 | (a1 << 2)) << (4 * j);
+        }
+        sgn = (sg | (sg >> 15)) & 0xffffu;
+        unsigned t = (cls | (cls >> 1)) & 0x55555555u;   // non-zero flags on the even bits, then squeezed together
+        t = (t | (t >> 1)) & 0x33333333u;
+        t = (t | (t >> 2)) & 0x0f0f0f0fu;
+        t = (t | (t >> 4)) & 0x00ff00ffu;
+        nzm = (t | (t >> 8)) & 0xffffu;
+    }
+#endif
     int kstart = 15;
     if (is_last) {
         kstart = nzm ? bitlen(nzm) - 1 : 0;
@@ -979,11 +1047,42 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
         const bool dc = first_cg && s != 4;                         // position 0 of a larger TU has its own context
         int k = is_last ? kstart - 1 : 15;
         const int kend = (!first_cg && (nzm & ~1u) == 0) ? 1 : 0;   // position 0 of a later group is inferred when it is the only one
+#if HEVCE_OPT_CTXFWD == 2
+        // software pipeline: the context byte of the next bin is loaded before the arithmetic of this one; when both bins
+        // share the context, the state comes from the register instead
+        if (k >= kend) {
+            auto ctx_of = [&](int kk) -> int { const int c0 = base + (int)((tab >> (4 * kk)) & 15u); return (dc && kk == 0) ? (int)CX_SIG : c0; };
+            int ci = ctx_of(k), v = cx[ci];
+            for (;;) {
+                const bool more = k > kend;
+                int cin = ci, vn = 0;
+                if (more) { cin = ctx_of(k - 1); vn = cx[cin]; }
+                const int nv = b.bin_step(tbl, (int)((nzm >> k) & 1u), v);
+                cx[ci] = (u8)nv;
+                if (!more) break;
+                v = cin == ci ? nv : vn;
+                ci = cin;
+                k--;
+            }
+        }
+#else
+#if HEVCE_OPT_CTXFWD
+        int pci = -1, pv = 0;
+#endif
         for (; k >= kend; k--) {
             int ci = base + (int)((tab >> (4 * k)) & 15u);
             if (dc && k == 0) ci = CX_SIG;
+#if HEVCE_OPT_CTXFWD
+            int v = cx[ci];
+            if (ci == pci) v = pv;
+            pv = b.bin_step(tbl, (int)((nzm >> k) & 1u), v);
+            cx[ci] = (u8)pv;
+            pci = ci;
+#else
             b.put_bin(tbl, (int)((nzm >> k) & 1u), cx[ci]);
+#endif
         }
+#endif
     }
     if (nzm) {
         // ---- greater1 / greater2 flags, signs (HEVCe.c:1229-1252)
@@ -991,13 +1090,24 @@ HEVCE_HD inline void code_group(BAC& b, const Tables& tbl, const Cx cx, int s, i
         int nz = 0, signs = 0, g2 = -1;
         c1 = 1;
         unsigned mm = nzm;
+#if HEVCE_OPT_CTXFWD == 1
+        int pc1 = -1, pv1 = 0;
+#endif
         while (mm) {
             const int k = bitlen(mm) - 1;
             mm &= ~(1u << k);
             signs = (signs << 1) | (int)((sgn >> k) & 1u);
             if (nz < 8) {
                 const int a = (int)((cls >> (2 * k)) & 3u), big = a > 1;
+#if HEVCE_OPT_CTXFWD == 1
+                int v1 = cx[CX_ONE + 4 * set + c1];
+                if (c1 == pc1) v1 = pv1;
+                pv1 = b.bin_step(tbl, big, v1);
+                cx[CX_ONE + 4 * set + c1] = (u8)pv1;
+                pc1 = c1;
+#else
                 b.put_bin(tbl, big, cx[CX_ONE + 4 * set + c1]);
+#endif
                 if (big) { c1 = 0; if (g2 < 0) g2 = a > 2; else g2 |= 4; }
                 else if (c1 > 0 && c1 < 3) c1++;
             }
@@ -1412,8 +1522,9 @@ HEVCE_HD inline int rdoq_level(int cf, const RdoqK& k, const Tables& tb, int& dl
     // wd * (dist(lvl-1) - dist(lvl)) < wb * (rate(lvl) - rate(lvl-1)); the rate step comes from an 8-entry table
     // (HEVCe.c:526-535: from level 7 on it is 65536 when lvl-5 is a power of two, else 0).  No product reaches 2^31.
     // tests/test_stages.py: every |cf| x TU size x qpd6 against the reference's quantize().
-    const int e0 = iabs(dl - (lvl << k.sh)) >> k.dsh;
-    const int e1 = (dl - ((lvl - 1) << k.sh)) >> k.dsh;
+    const int r = dl - (lvl << k.sh);                           // in [-add, add)
+    const int e0 = iabs(r) >> k.dsh;
+    const int e1 = (r + 2 * k.add) >> k.dsh;                    // distance to lvl-1: positive
     const int d0 = (e0 * e0) >> 7;
     const int d1 = (e1 < 46340 ? e1 * e1 : IMAX) >> 7;          // saturates at qpd6 = 4 only
     const int dr = tb.drate[imin(lvl, 7)] + ((lvl >= 7 && ((lvl - 5) & (lvl - 6)) == 0) ? 65536 : 0);

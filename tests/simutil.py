@@ -27,7 +27,8 @@ def _build(src, so, variant, extra=()):
     srcs = [os.path.join(SIM_DIR, src), os.path.join(CSRC, "hevce_core.h"), os.path.join(CSRC, "hevce_xform_gen.h")]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
         return
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", *extra, *variant_flags(variant), "-I", CSRC, "-o", so, srcs[0]], check=True)
+    xflags = os.environ.get("HEVCE_SIM_XFLAGS", "").split()   # development: extra -DHEVCE_OPT_... switches for an A/B candidate
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", *extra, *variant_flags(variant), *xflags, "-I", CSRC, "-o", so, srcs[0]], check=True)
 
 
 def build_sim(force=False, variant="g7"):
