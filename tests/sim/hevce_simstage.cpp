@@ -5,6 +5,7 @@
 //                          dequantisation -> inverse transform -> reconstruction + SSE of ONE candidate (phases border, A-D)
 //   hevce_stage_residual : residual_coding() of one TU from a fresh coder and fresh contexts (put_residual)
 //   hevce_stage_rdoq     : the per-coefficient RDOQ decision (rdoq_level) for a list of coefficients
+//   hevce_stage_tables   : the coder tables of the kernel (bin table, rate steps, initial contexts) as plain integers
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -85,6 +86,21 @@ extern "C" void hevce_stage_rdoq(int T, int q, int n, const int* cf, int* lev) {
         const int pick = rdoq_level(cf[i], k, tb, dl);
         lev[i] = cf[i] < 0 ? -pick : pick;
     }
+}
+
+// Kernel tables as integers.  st: [128][6] = LPS range for range quarter 0..3, context after an LPS, context after an MPS
+// (Tables::st8); drate: [8] (Tables::drate); ctx: [5][4 * CTXW] initial context bytes for qpd6 = 0..4 in the compact layout.
+extern "C" int hevce_stage_tables(int* st, int* drate, int* ctx) {
+    const Tables& tb = *tables();
+    for (int v = 0; v < 128; v++) {
+        for (int q = 0; q < 4; q++) st[v * 6 + q] = (int)((tb.st8[v] >> (8 * q)) & 0xff);
+        st[v * 6 + 4] = (int)((tb.st8[v] >> 32) & 0xff);
+        st[v * 6 + 5] = (int)((tb.st8[v] >> 40) & 0xff);
+    }
+    for (int i = 0; i < 8; i++) drate[i] = tb.drate[i];
+    for (int q = 0; q < 5; q++)
+        for (int i = 0; i < 4 * CTXW; i++) ctx[q * 4 * CTXW + i] = ctx_init_value(tb.ctx_iv[i], q);
+    return 4 * CTXW;
 }
 
 // lev: T*T raster levels.  state: {range, low, nbits, nbytes, held, z, n} at the end.  returns the bits written.

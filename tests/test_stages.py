@@ -148,6 +148,54 @@ def test_rdoq_every_coefficient_value(libs, T):
         assert len(bad) == 0, (T, q, int(vals[bad[0]]), int(got[bad[0]]), int(want[bad[0]]))
 
 
+def test_coder_tables_match_the_reference_tables(libs):
+    """The kernel's packed tables against the arrays and functions the reference exports: the 64-bit word per context
+    state (LPS ranges, both next states: CABAC_LPS_TABLE, CONTEXT_NEXT_STATE_LPS / _MPS, HEVCe.c:701-713), the
+    renormalisation shift the kernel derives from the LPS range (CABAC_RENORM_TABLE, :715), the RDOQ rate steps
+    (estimateCoeffRate, :522) and the initial value of every context of the compact layout (newContextSet, :763)."""
+    ours, ref = libs
+    st, dr, cx = (ctypes.c_int * (128 * 6))(), (ctypes.c_int * 8)(), (ctypes.c_int * (5 * 92))()
+    n = ours.hevce_stage_tables(st, dr, cx)
+    assert n == 92
+    lps = (ctypes.c_ubyte * 256).in_dll(ref, "CABAC_LPS_TABLE")
+    renorm = (ctypes.c_ubyte * 32).in_dll(ref, "CABAC_RENORM_TABLE")
+    nlps = (ctypes.c_ubyte * 128).in_dll(ref, "CONTEXT_NEXT_STATE_LPS")
+    nmps = (ctypes.c_ubyte * 128).in_dll(ref, "CONTEXT_NEXT_STATE_MPS")
+    for v in range(128):
+        for q in range(4):
+            r = st[v * 6 + q]
+            assert r == lps[(v >> 1) * 4 + q], (v, q)
+            if v < 126:   # probability state 63 is reserved for the terminate bin (no context ever holds it)
+                assert 9 - r.bit_length() == renorm[r >> 3], (v, q, r)
+        assert (st[v * 6 + 4], st[v * 6 + 5]) == (nlps[v], nmps[v]), v
+    ref.estimateCoeffRate.restype = ctypes.c_int
+    rate = [ref.estimateCoeffRate(l) for l in range(0, 9000)]
+    for l in range(1, 9000):      # levels reach 8192 (|coefficient| <= 32767 at qpd6 = 0, 32x32)
+        step = dr[min(l, 7)] + (65536 if l >= 7 and ((l - 5) & (l - 6)) == 0 else 0)
+        assert step == rate[l] - rate[l - 1], l
+    # compact context index -> byte offset in the reference's ContextSet (HEVCe.c:745-759)
+    m = {}
+    for i in range(3):
+        m[0 + i], m[3 + i] = 16 + i, 41 + i                       # last_x / last_y of 4x4 TUs
+    for i in range(16):
+        m[6 + i] = 112 + i                                        # greater1
+    for i in range(4):
+        m[22 + i] = 136 + i                                       # greater2
+    for i in range(27):
+        m[26 + i] = 68 + i                                        # sig_coeff (luma)
+    for i in range(12):
+        m[53 + i] = i                                             # split_cu .. cbf_chroma[0]
+    m[65], m[66] = 66, 67                                         # coded_sub_block
+    for row, (off, cnt) in enumerate([(0, 3), (3, 4), (7, 5)], start=1):
+        for i in range(cnt):
+            m[67 + off + i], m[79 + off + i] = 16 + 5 * row + i, 41 + 5 * row + i
+    assert sorted(m) == list(range(91))
+    for q in range(5):
+        want = ref.newContextSet(q)
+        for i, o in m.items():
+            assert cx[q * 92 + i] == want.b[o], (q, i, o)
+
+
 def ref_residual(ref, T, mode, q, lev):
     cab, ctx = ref.newCABACcoder(), ref.newContextSet(q)
     blk = np.zeros((32, 32), np.int32)
