@@ -104,10 +104,12 @@ static hevce_session *pool_acquire(int device, int *slot) {
     pthread_mutex_unlock(&g_lock);
     if (!s) {   /* an empty pool slot, or every pooled session is busy (then the session is temporary) */
         s = hevce_session_create_empty(device);
-        if (s && *slot >= 0) {
+        if (*slot >= 0) {
             pthread_mutex_lock(&g_lock);
-            g_pool[device][*slot] = s;
+            if (s) g_pool[device][*slot] = s;
+            else g_pool_busy[device][*slot] = 0;   /* creation failed: the slot is free again */
             pthread_mutex_unlock(&g_lock);
+            if (!s) *slot = -1;
         }
     }
     return s;
@@ -264,7 +266,7 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
                               unsigned char *const *img_rcons, int *ysz, int *xsz, const int *qpd6, int *stream_len) {
     Shard shards[MAX_DEV];
     pthread_t threads[MAX_DEV];
-    int ndev, devs[MAX_DEV], i, k, nshard = 0, status = 0, *lens = stream_len, saved_device;
+    int ndev, devs[MAX_DEV], started[MAX_DEV], i, k, nshard = 0, status = 0, *lens = stream_len, saved_device;
     const int max_dim = hevce_get_max_dim();   /* one value for the whole call: sharding, clamp and size write-back */
     long long total = 0, acc = 0;
     if (n < 0) return HEVCE_ERR_ARG;
@@ -297,11 +299,13 @@ API int HEVCImageEncoderBatch(int n, unsigned char *const *pbuffers, const unsig
         shards[nshard].ysz = ysz; shards[nshard].xsz = xsz; shards[nshard].qpd6 = qpd6; shards[nshard].stream_len = lens;
         nshard++;
     }
-    for (k = 1; k < nshard; k++)
-        if (pthread_create(&threads[k], NULL, shard_main, &shards[k])) { threads[k] = 0; shard_main(&shards[k]); }
+    for (k = 1; k < nshard; k++) {
+        started[k] = pthread_create(&threads[k], NULL, shard_main, &shards[k]) == 0;
+        if (!started[k]) shard_main(&shards[k]);   /* no thread: run the shard here */
+    }
     shard_main(&shards[0]);
     for (k = 1; k < nshard; k++)
-        if (threads[k]) pthread_join(threads[k], NULL);
+        if (started[k]) pthread_join(threads[k], NULL);
     for (k = 0; k < nshard; k++)
         if (shards[k].status && !status) status = shards[k].status;
     if (!status)
