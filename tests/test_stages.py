@@ -168,6 +168,9 @@ def test_coder_tables_match_the_reference_tables(libs):
             if v < 126:   # probability state 63 is reserved for the terminate bin (no context ever holds it)
                 assert 9 - r.bit_length() == renorm[r >> 3], (v, q, r)
         assert (st[v * 6 + 4], st[v * 6 + 5]) == (nlps[v], nmps[v]), v
+    # probability state 63 (context bytes 126, 127) is closed off: no transition from a lower state and no initial value reaches it
+    assert all(st[v * 6 + 4] < 126 and st[v * 6 + 5] < 126 for v in range(126))
+    assert all(cx[i] < 126 for i in range(5 * 92))
     ref.estimateCoeffRate.restype = ctypes.c_int
     rate = [ref.estimateCoeffRate(l) for l in range(0, 9000)]
     for l in range(1, 9000):      # levels reach 8192 (|coefficient| <= 32767 at qpd6 = 0, 32x32)
